@@ -1,0 +1,247 @@
+"""Context-parallel attention plans.
+
+Every sharding scheme of the reference is a statement about *global token positions*:
+
+* ring      - rank r holds positions ``[r*L, (r+1)*L)``            (ring_flash_attn.py:26-63)
+* zigzag    - rank r holds chunks ``r`` and ``2W-1-r`` of ``2W``    (zigzag_ring_flash_attn.py:60-84)
+* stripe    - rank r holds positions ``r, r+W, r+2W, ...``          (stripe_flash_attn.py:29-97)
+* varlen    - the same, independently per packed document           (ring_flash_attn_varlen.py:56-59,
+                                                                    zigzag_ring_flash_attn_varlen.py:99-108)
+* llama3    - contiguous split of the flat token stream             (llama3_flash_attn_varlen.py:10-60)
+
+Instead of hand-writing a per-scheme step loop, this module turns (scheme, rank, world, shapes,
+cu_seqlens) into a *plan*: local query chunks plus, for every source rank, the key segments each
+chunk may see and the diagonal offset of the causal boundary (key ``j`` visible to query ``i`` iff
+``j <= i + diag``).  The torch fallback executes a plan with ``ops.dense.block_fwd``; the sm_100a
+kernels consume the very same plan as a device table and compute the masks in-kernel.
+
+Rows are token-major: a batch tensor ``(B, S_l, H, D)`` is the row range ``[b*S_l, (b+1)*S_l)``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+
+@dataclass(frozen=True)
+class QChunk:
+    row0: int  # first local query row
+    rows: int  # number of rows (contiguous, contiguous positions)
+
+
+@dataclass(frozen=True)
+class Segment:
+    chunk: int  # index into CPPlan.q_chunks
+    src: int  # source rank (within the CP group) that owns the keys
+    kv_row0: int  # first row inside the source rank's local K/V
+    kv_len: int
+    diag: Optional[int]  # None = fully visible; else key j visible to query i iff j <= i + diag
+
+
+@dataclass
+class CPPlan:
+    world: int
+    rank: int
+    q_rows: int  # local query rows
+    kv_rows: int  # local key rows on every rank (shards are equal sized)
+    q_chunks: List[QChunk] = field(default_factory=list)
+    segments: List[Segment] = field(default_factory=list)
+
+    def by_src(self) -> Dict[int, List[Segment]]:
+        out: Dict[int, List[Segment]] = {}
+        for s in self.segments:
+            out.setdefault(s.src, []).append(s)
+        return out
+
+    def needed_kv_rows(self, src: int) -> Optional[Tuple[int, int]]:
+        """[lo, hi) row range of ``src``'s shard that this rank reads, or None if nothing."""
+        segs = [s for s in self.segments if s.src == src]
+        if not segs:
+            return None
+        return min(s.kv_row0 for s in segs), max(s.kv_row0 + s.kv_len for s in segs)
+
+    def flops(self, heads_q: int, head_dim: int) -> int:
+        """Forward matmul FLOPs of this rank's share (2 GEMMs, masked area excluded)."""
+        total = 0
+        for s in self.segments:
+            n = self.q_chunks[s.chunk].rows
+            total += visible_area(n, s.kv_len, s.diag)
+        return 4 * total * heads_q * head_dim
+
+
+def visible_area(q_len: int, kv_len: int, diag: Optional[int]) -> int:
+    """Number of (query, key) pairs with ``j <= i + diag`` in a q_len x kv_len block."""
+    if diag is None:
+        return q_len * kv_len
+    lo = max(0, -diag)  # first row that sees at least one key
+    full_from = max(lo, kv_len - 1 - diag)  # first row that sees every key
+    ramp_hi = min(q_len, full_from)
+    area = 0
+    if ramp_hi > lo:
+        area += ((lo + diag + 1) + (ramp_hi - 1 + diag + 1)) * (ramp_hi - lo) // 2
+    if q_len > full_from:
+        area += (q_len - full_from) * kv_len
+    return area
+
+
+def _classify(q_pos0: int, q_len: int, k_pos0: int, k_len: int, causal: bool, stride: int = 1,
+              q_phase: int = 0, k_phase: int = 0):
+    """Visibility of a key run against a query run.  Returns "skip", None (full) or an int diag.
+
+    Positions are ``pos0 + idx * stride + phase``.  stride > 1 is the striped layout."""
+    if not causal:
+        return None
+    if stride == 1:
+        diag = q_pos0 - k_pos0
+    else:
+        # j*W + rk <= i*W + rq  <=>  j <= i + floor((rq - rk) / W) + (q_pos0 - k_pos0)
+        diag = (q_pos0 - k_pos0) + (0 if k_phase <= q_phase else -1)
+    if diag + (q_len - 1) < 0:
+        return "skip"
+    if diag >= k_len - 1:
+        return None
+    return diag
+
+
+def _add(plan: CPPlan, chunk: int, src: int, kv_row0: int, kv_len: int, vis) -> None:
+    if vis == "skip" or kv_len <= 0:
+        return
+    # coalesce with the previous segment when it continues the same key run on the same diagonal
+    if plan.segments:
+        p = plan.segments[-1]
+        if p.chunk == chunk and p.src == src and p.kv_row0 + p.kv_len == kv_row0:
+            if p.diag is None and vis is None:
+                plan.segments[-1] = Segment(chunk, src, p.kv_row0, p.kv_len + kv_len, None)
+                return
+            if p.diag is not None and vis is not None and vis == p.diag - p.kv_len:
+                plan.segments[-1] = Segment(chunk, src, p.kv_row0, p.kv_len + kv_len, p.diag)
+                return
+    plan.segments.append(Segment(chunk, src, kv_row0, kv_len, vis))
+
+
+def _src_order(rank: int, world: int) -> List[int]:
+    # ring schedule: own shard first, then the shard that started 1, 2, ... hops upstream
+    return [(rank - s) % world for s in range(world)]
+
+
+# ----------------------------------------------------------------------------------------------
+# batch layouts
+# ----------------------------------------------------------------------------------------------
+
+def plan_ring(rank: int, world: int, batch: int, seqlen_local: int, causal: bool) -> CPPlan:
+    L = seqlen_local
+    plan = CPPlan(world, rank, batch * L, batch * L)
+    for b in range(batch):
+        plan.q_chunks.append(QChunk(b * L, L))
+    for src in _src_order(rank, world):
+        for b in range(batch):
+            _add(plan, b, src, b * L, L, _classify(rank * L, L, src * L, L, causal))
+    return plan
+
+
+def plan_zigzag(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
+    L = seqlen_local
+    if L % 2:
+        raise ValueError("zigzag needs an even local sequence length")
+    c = L // 2
+    plan = CPPlan(world, rank, batch * L, batch * L)
+    for b in range(batch):
+        plan.q_chunks.append(QChunk(b * L, c))
+        plan.q_chunks.append(QChunk(b * L + c, c))
+    qpos = (rank * c, (2 * world - 1 - rank) * c)
+    for src in _src_order(rank, world):
+        kpos = (src * c, (2 * world - 1 - src) * c)
+        for b in range(batch):
+            for qi in range(2):
+                for ki in range(2):
+                    _add(plan, 2 * b + qi, src, b * L + ki * c, c,
+                         _classify(qpos[qi], c, kpos[ki], c, True))
+    return plan
+
+
+def plan_stripe(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
+    L = seqlen_local
+    plan = CPPlan(world, rank, batch * L, batch * L)
+    for b in range(batch):
+        plan.q_chunks.append(QChunk(b * L, L))
+    for src in _src_order(rank, world):
+        for b in range(batch):
+            _add(plan, b, src, b * L, L,
+                 _classify(0, L, 0, L, True, stride=world, q_phase=rank, k_phase=src))
+    return plan
+
+
+# ----------------------------------------------------------------------------------------------
+# varlen layouts (one shared local cu_seqlens; every document is split evenly over the ranks)
+# ----------------------------------------------------------------------------------------------
+
+def plan_ring_varlen(rank: int, world: int, cu_seqlens: Sequence[int], causal: bool) -> CPPlan:
+    cu = [int(x) for x in cu_seqlens]
+    total = cu[-1]
+    plan = CPPlan(world, rank, total, total)
+    for a, b in zip(cu[:-1], cu[1:]):
+        plan.q_chunks.append(QChunk(a, b - a))
+    for src in _src_order(rank, world):
+        for d, (a, b) in enumerate(zip(cu[:-1], cu[1:])):
+            n = b - a
+            _add(plan, d, src, a, n, _classify(rank * n, n, src * n, n, causal))
+    return plan
+
+
+def plan_zigzag_varlen(rank: int, world: int, cu_seqlens: Sequence[int]) -> CPPlan:
+    cu = [int(x) for x in cu_seqlens]
+    total = cu[-1]
+    plan = CPPlan(world, rank, total, total)
+    for a, b in zip(cu[:-1], cu[1:]):
+        if (b - a) % 2:
+            raise ValueError("zigzag varlen needs every local document length to be even")
+        c = (b - a) // 2
+        plan.q_chunks.append(QChunk(a, c))
+        plan.q_chunks.append(QChunk(a + c, c))
+    for src in _src_order(rank, world):
+        for d, (a, b) in enumerate(zip(cu[:-1], cu[1:])):
+            c = (b - a) // 2
+            qpos = (rank * c, (2 * world - 1 - rank) * c)
+            kpos = (src * c, (2 * world - 1 - src) * c)
+            for qi in range(2):
+                for ki in range(2):
+                    _add(plan, 2 * d + qi, src, a + ki * c, c,
+                         _classify(qpos[qi], c, kpos[ki], c, True))
+    return plan
+
+
+# ----------------------------------------------------------------------------------------------
+# llama3 layout (contiguous split of the flat stream; documents may straddle ranks)
+# ----------------------------------------------------------------------------------------------
+
+def plan_llama3(rank: int, world: int, tokens_local: int, cu_seqlens_q: Sequence[int],
+                cu_seqlens_k: Sequence[int], k_slice_start: int, causal: bool) -> CPPlan:
+    """Plan from the outputs of ``llama3_flash_attn_prepare_cu_seqlens``.
+
+    ``cu_seqlens_k`` is relative to ``k_slice_start`` in the *global* (gathered) key stream; the
+    causal mask is bottom-right aligned per document (llama3_flash_attn_varlen.py:44-48)."""
+    cuq = [int(x) for x in cu_seqlens_q]
+    cuk = [int(x) for x in cu_seqlens_k]
+    L = tokens_local
+    plan = CPPlan(world, rank, L, L)
+    for a, b in zip(cuq[:-1], cuq[1:]):
+        plan.q_chunks.append(QChunk(a, b - a))
+    pieces = []  # (src, doc, kv_row0, len, vis)
+    for d in range(len(cuq) - 1):
+        qn = cuq[d + 1] - cuq[d]
+        k0 = k_slice_start + cuk[d]
+        k1 = k_slice_start + cuk[d + 1]
+        kn = k1 - k0
+        base_diag = kn - qn  # bottom-right alignment
+        for src in range(world):
+            lo, hi = max(k0, src * L), min(k1, (src + 1) * L)
+            if hi <= lo:
+                continue
+            # key j' (within this piece) is doc key j' + (lo - k0)
+            vis = _classify(base_diag, qn, lo - k0, hi - lo, causal) if causal else None
+            pieces.append((src, d, lo - src * L, hi - lo, vis))
+    for src in _src_order(rank, world):
+        for (s, d, r0, n, vis) in pieces:
+            if s == src:
+                _add(plan, d, src, r0, n, vis)
+    return plan

@@ -1,0 +1,295 @@
+"""Public attention entry points - the 18 functions of the reference plus ``prepare``.
+
+Signatures, defaults and return values follow the reference exactly
+(/root/reference/ring_flash_attn/__init__.py:1-35; batch: ring_flash_attn.py:223-301,
+zigzag_ring_flash_attn.py:268-346, stripe_flash_attn.py:300-378; varlen:
+ring_flash_attn_varlen.py:268-358, zigzag_ring_flash_attn_varlen.py:415-505,
+llama3_flash_attn_varlen.py:390-504) so a user can switch by changing the import.
+
+Unlike the reference there is a single autograd bridge: each scheme only contributes a *plan*
+(``ops/plan.py``); the engine (``parallel/engine.py``) runs it on the fused sm_100a path or on the
+torch.distributed fallback.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Optional, Tuple
+
+import torch
+
+from ..ops import plan as P
+from . import engine
+from .comm import group_info
+
+__all__ = [
+    "ring_flash_attn_func", "ring_flash_attn_kvpacked_func", "ring_flash_attn_qkvpacked_func",
+    "zigzag_ring_flash_attn_func", "zigzag_ring_flash_attn_kvpacked_func", "zigzag_ring_flash_attn_qkvpacked_func",
+    "stripe_flash_attn_func", "stripe_flash_attn_kvpacked_func", "stripe_flash_attn_qkvpacked_func",
+    "ring_flash_attn_varlen_func", "ring_flash_attn_varlen_kvpacked_func", "ring_flash_attn_varlen_qkvpacked_func",
+    "zigzag_ring_flash_attn_varlen_func", "zigzag_ring_flash_attn_varlen_kvpacked_func",
+    "zigzag_ring_flash_attn_varlen_qkvpacked_func",
+    "llama3_flash_attn_varlen_func", "llama3_flash_attn_varlen_kvpacked_func",
+    "llama3_flash_attn_varlen_qkvpacked_func", "llama3_flash_attn_prepare_cu_seqlens",
+]
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd bridge
+# ----------------------------------------------------------------------------------------------
+
+class CPAttention(torch.autograd.Function):
+    """One bridge for every scheme.  Inputs are token-major: q (T,Hq,D), k/v (T,Hkv,D)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, plan, scale, group, transport, heads_k_stride, deterministic):
+        out, lse = engine.cp_forward(plan, q, k, v, scale, group, transport, heads_k_stride)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.plan, ctx.scale, ctx.group = plan, scale, group
+        ctx.transport, ctx.heads_k_stride, ctx.deterministic = transport, heads_k_stride, deterministic
+        ctx.mark_non_differentiable(lse)
+        return out, lse
+
+    @staticmethod
+    def backward(ctx, dout, _dlse):
+        q, k, v, out, lse = ctx.saved_tensors
+        dq, dk, dv = engine.cp_backward(ctx.plan, dout, q, k, v, out, lse, ctx.scale, ctx.group,
+                                        ctx.transport, ctx.heads_k_stride, ctx.deterministic)
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+def _check_common(q, dropout_p, window_size, alibi_slopes):
+    if alibi_slopes is not None:
+        raise NotImplementedError("alibi_slopes is not supported (same as the reference)")
+    if dropout_p != 0.0:
+        raise NotImplementedError("dropout_p > 0 is not supported by context-parallel attention")
+    if tuple(window_size) != (-1, -1):
+        raise NotImplementedError("window_size (sliding window) is not supported across shards")
+
+
+def _scale(q, softmax_scale):
+    return q.shape[-1] ** (-0.5) if softmax_scale is None else float(softmax_scale)
+
+
+_CU_CACHE = {}
+
+
+def cu_seqlens_to_host(cu: torch.Tensor) -> Tuple[int, ...]:
+    """Host copy of a cu_seqlens tensor; device tensors are read once per (storage, version)."""
+    if not isinstance(cu, torch.Tensor):
+        return tuple(int(x) for x in cu)
+    if cu.device.type == "cpu":
+        return tuple(int(x) for x in cu.tolist())
+    key = (cu.data_ptr(), cu._version, cu.numel(), cu.device.index)
+    hit = _CU_CACHE.get(key)
+    if hit is None:
+        if len(_CU_CACHE) > 256:
+            _CU_CACHE.clear()
+        hit = tuple(int(x) for x in cu.tolist())
+        _CU_CACHE[key] = hit
+    return hit
+
+
+@functools.lru_cache(maxsize=512)
+def _batch_plan(scheme, rank, world, batch, seqlen, causal):
+    if scheme == "ring":
+        return P.plan_ring(rank, world, batch, seqlen, causal)
+    if scheme == "zigzag":
+        return P.plan_zigzag(rank, world, batch, seqlen)
+    if scheme == "stripe":
+        return P.plan_stripe(rank, world, batch, seqlen)
+    raise ValueError(scheme)
+
+
+@functools.lru_cache(maxsize=512)
+def _varlen_plan(scheme, rank, world, cu, causal):
+    if scheme == "ring":
+        return P.plan_ring_varlen(rank, world, cu, causal)
+    if scheme == "zigzag":
+        return P.plan_zigzag_varlen(rank, world, cu)
+    raise ValueError(scheme)
+
+
+@functools.lru_cache(maxsize=512)
+def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal):
+    return P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal)
+
+
+def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
+               deterministic, return_attn_probs, group):
+    _check_common(q, dropout_p, window_size, alibi_slopes)
+    if scheme in ("zigzag", "stripe") and not causal:
+        raise AssertionError(f"{scheme} attention only supports causal=True (as in the reference)")
+    rank, world = group_info(group)
+    b, s, hq, d = q.shape
+    plan = _batch_plan(scheme, rank, world, b, s, bool(causal))
+    out, lse = CPAttention.apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
+                                 v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
+                                 "ring", 1, deterministic)
+    out = out.view(b, s, hq, d)
+    if not return_attn_probs:
+        return out
+    return out, lse.view(hq, b, s).permute(1, 0, 2).contiguous(), None
+
+
+def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scale, causal, window_size,
+                alibi_slopes, deterministic, return_attn_probs, group):
+    _check_common(q, dropout_p, window_size, alibi_slopes)
+    if scheme == "zigzag" and not causal:
+        raise AssertionError("zigzag attention only supports causal=True (as in the reference)")
+    rank, world = group_info(group)
+    plan = _varlen_plan(scheme, rank, world, cu_seqlens_to_host(cu_seqlens), bool(causal))
+    if plan.q_rows != q.shape[0]:
+        raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
+    out, lse = CPAttention.apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic)
+    return (out, lse, None) if return_attn_probs else out
+
+
+# ----------------------------------------------------------------------------------------------
+# batch layout: ring / zigzag / stripe
+# ----------------------------------------------------------------------------------------------
+
+def _define_batch(scheme, prefix):
+    def func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
+             alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None):
+        return _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
+                          deterministic, return_attn_probs, group)
+
+    def kvpacked_func(q, kv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
+                      alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None):
+        return _run_batch(scheme, q, kv[:, :, 0], kv[:, :, 1], dropout_p, softmax_scale, causal,
+                          window_size, alibi_slopes, deterministic, return_attn_probs, group)
+
+    def qkvpacked_func(qkv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
+                       alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None):
+        return _run_batch(scheme, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dropout_p, softmax_scale,
+                          causal, window_size, alibi_slopes, deterministic, return_attn_probs, group)
+
+    doc = ("{name}: q (B, S_local, Hq, D), k/v (B, S_local, Hkv, D) [kv (B,S_local,2,Hkv,D); "
+           "qkv (B,S_local,3,H,D)] sharded with the '" + scheme + "' layout over `group`.  Returns out "
+           "(and (out, softmax_lse (B,Hq,S_local), None) when return_attn_probs).")
+    for f, suffix in ((func, "func"), (kvpacked_func, "kvpacked_func"), (qkvpacked_func, "qkvpacked_func")):
+        f.__name__ = f.__qualname__ = f"{prefix}_flash_attn_{suffix}"
+        f.__doc__ = doc.format(name=f.__name__)
+    return func, kvpacked_func, qkvpacked_func
+
+
+ring_flash_attn_func, ring_flash_attn_kvpacked_func, ring_flash_attn_qkvpacked_func = _define_batch("ring", "ring")
+(zigzag_ring_flash_attn_func, zigzag_ring_flash_attn_kvpacked_func,
+ zigzag_ring_flash_attn_qkvpacked_func) = _define_batch("zigzag", "zigzag_ring")
+stripe_flash_attn_func, stripe_flash_attn_kvpacked_func, stripe_flash_attn_qkvpacked_func = _define_batch(
+    "stripe", "stripe")
+
+
+# ----------------------------------------------------------------------------------------------
+# varlen layout: ring / zigzag
+# ----------------------------------------------------------------------------------------------
+
+def _define_varlen(scheme, prefix):
+    def func(q, k, v, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False,
+             window_size=(-1, -1), alibi_slopes=None, deterministic=False, return_attn_probs=False,
+             group=None):
+        return _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scale, causal,
+                           window_size, alibi_slopes, deterministic, return_attn_probs, group)
+
+    def kvpacked_func(q, kv, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False,
+                      window_size=(-1, -1), alibi_slopes=None, deterministic=False,
+                      return_attn_probs=False, group=None):
+        return _run_varlen(scheme, q, kv[:, 0], kv[:, 1], cu_seqlens, max_seqlen, dropout_p, softmax_scale,
+                           causal, window_size, alibi_slopes, deterministic, return_attn_probs, group)
+
+    def qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False,
+                       window_size=(-1, -1), alibi_slopes=None, deterministic=False,
+                       return_attn_probs=False, group=None):
+        return _run_varlen(scheme, qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens, max_seqlen, dropout_p,
+                           softmax_scale, causal, window_size, alibi_slopes, deterministic,
+                           return_attn_probs, group)
+
+    doc = ("{name}: packed q (T_local, Hq, D), k/v (T_local, Hkv, D) with ONE local cu_seqlens "
+           "(global cu_seqlens // world_size); every document is sharded with the '" + scheme +
+           "' layout.  Returns out (and (out, softmax_lse (Hq,T_local), None) when return_attn_probs).")
+    for f, suffix in ((func, "func"), (kvpacked_func, "kvpacked_func"), (qkvpacked_func, "qkvpacked_func")):
+        f.__name__ = f.__qualname__ = f"{prefix}_flash_attn_varlen_{suffix}"
+        f.__doc__ = doc.format(name=f.__name__)
+    return func, kvpacked_func, qkvpacked_func
+
+
+(ring_flash_attn_varlen_func, ring_flash_attn_varlen_kvpacked_func,
+ ring_flash_attn_varlen_qkvpacked_func) = _define_varlen("ring", "ring")
+(zigzag_ring_flash_attn_varlen_func, zigzag_ring_flash_attn_varlen_kvpacked_func,
+ zigzag_ring_flash_attn_varlen_qkvpacked_func) = _define_varlen("zigzag", "zigzag_ring")
+
+
+# ----------------------------------------------------------------------------------------------
+# llama3 (all-gather style context parallelism, varlen only)
+# ----------------------------------------------------------------------------------------------
+
+def llama3_flash_attn_prepare_cu_seqlens(cu_seqlens: torch.Tensor, causal: bool, rank: int, world_size: int):
+    """Per-rank cu_seqlens for the llama3 layout (flat token stream split contiguously).
+
+    Same outputs as the reference (/root/reference/ring_flash_attn/llama3_flash_attn_varlen.py:10-60):
+    ``(cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, local_k_slice)``.  The arithmetic is
+    done once on the host (one device read instead of the reference's seven ``.item()`` syncs)."""
+    cu = list(cu_seqlens_to_host(cu_seqlens))
+    total = cu[-1]
+    if total % world_size:
+        raise AssertionError("total length must be divisible by world_size")
+    L = total // world_size
+    lo, hi = rank * L, (rank + 1) * L
+    # documents overlapping [lo, hi): first doc whose end is > lo ... last doc whose start is < hi
+    left = max(i for i in range(len(cu) - 1) if cu[i] <= lo)
+    right = min(i for i in range(1, len(cu)) if cu[i] >= hi)
+    window = cu[left:right + 1]
+    cu_q = [min(max(x - lo, 0), L) for x in window]
+    cu_q[0], cu_q[-1] = 0, L
+    slice_left = cu[left]
+    slice_right = hi if causal else cu[right]
+    cu_k = list(window)
+    cu_k[-1] = slice_right
+    cu_k = [x - slice_left for x in cu_k]
+    dev = cu_seqlens.device if isinstance(cu_seqlens, torch.Tensor) else None
+    dt = cu_seqlens.dtype if isinstance(cu_seqlens, torch.Tensor) else torch.int32
+    cu_q_t = torch.tensor(cu_q, dtype=dt, device=dev)
+    cu_k_t = torch.tensor(cu_k, dtype=dt, device=dev)
+    _CU_CACHE[(cu_q_t.data_ptr(), cu_q_t._version, cu_q_t.numel(), cu_q_t.device.index)] = tuple(cu_q)
+    _CU_CACHE[(cu_k_t.data_ptr(), cu_k_t._version, cu_k_t.numel(), cu_k_t.device.index)] = tuple(cu_k)
+    max_q = max(b - a for a, b in zip(cu_q[:-1], cu_q[1:]))
+    max_k = max(b - a for a, b in zip(cu_k[:-1], cu_k[1:]))
+    return cu_q_t, cu_k_t, max_q, max_k, slice(slice_left, slice_right)
+
+
+def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                                  heads_k_stride, local_k_slice, dropout_p=0.0, softmax_scale=None,
+                                  causal=False, window_size=(-1, -1), alibi_slopes=None,
+                                  deterministic=False, return_attn_probs=False, group=None):
+    """llama3-style CP: q/k/v (T_local, H*, D) are a contiguous slice of the flat token stream; the
+    cu_seqlens / local_k_slice come from :func:`llama3_flash_attn_prepare_cu_seqlens`."""
+    _check_common(q, dropout_p, window_size, alibi_slopes)
+    rank, world = group_info(group)
+    k_start = local_k_slice.start or 0
+    plan = _llama3_plan(rank, world, q.shape[0], cu_seqlens_to_host(cu_seqlens_q),
+                        cu_seqlens_to_host(cu_seqlens_k), int(k_start), bool(causal))
+    out, lse = CPAttention.apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
+                                 int(heads_k_stride), deterministic)
+    return (out, lse, None) if return_attn_probs else out
+
+
+def llama3_flash_attn_varlen_kvpacked_func(q, kv, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                                           heads_k_stride, local_k_slice, dropout_p=0.0, softmax_scale=None,
+                                           causal=False, window_size=(-1, -1), alibi_slopes=None,
+                                           deterministic=False, return_attn_probs=False, group=None):
+    """kv (T_local, 2, Hkv, D) variant of :func:`llama3_flash_attn_varlen_func`."""
+    return llama3_flash_attn_varlen_func(q, kv[:, 0], kv[:, 1], cu_seqlens_q, cu_seqlens_k, max_seqlen_q,
+                                         max_seqlen_k, heads_k_stride, local_k_slice, dropout_p, softmax_scale,
+                                         causal, window_size, alibi_slopes, deterministic, return_attn_probs,
+                                         group)
+
+
+def llama3_flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                                            heads_k_stride, local_k_slice, dropout_p=0.0, softmax_scale=None,
+                                            causal=False, window_size=(-1, -1), alibi_slopes=None,
+                                            deterministic=False, return_attn_probs=False, group=None):
+    """qkv (T_local, 3, H, D) variant of :func:`llama3_flash_attn_varlen_func`."""
+    return llama3_flash_attn_varlen_func(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens_q, cu_seqlens_k,
+                                         max_seqlen_q, max_seqlen_k, heads_k_stride, local_k_slice, dropout_p,
+                                         softmax_scale, causal, window_size, alibi_slopes, deterministic,
+                                         return_attn_probs, group)

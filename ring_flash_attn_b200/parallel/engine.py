@@ -1,0 +1,260 @@
+"""Plan executors: run a :class:`~ring_flash_attn_b200.ops.plan.CPPlan` forward and backward.
+
+Two transports, selected per call:
+
+* ``fused``   - sm_100a kernels; K/V shards are pulled from the owners' peer-mapped memory inside
+                the attention kernel itself and dK/dV partials are pushed back the same way
+                (``parallel/fused.py``).  Used whenever the tensors live on a Blackwell GPU.
+* ``ring`` / ``allgather`` - torch.distributed fallback (gloo on CPU, NCCL on GPUs without peer
+                access): the reference's own communication pattern
+                (/root/reference/ring_flash_attn/ring_flash_attn.py:26-63,97-152 and
+                llama3_flash_attn_varlen.py:89-158,218-297) around ``ops.dense`` blocks (CPU) or the
+                single-GPU sm_100a kernel (CUDA).
+
+All tensors here are token-major: q ``(Tq,Hq,D)``, k/v ``(Tk,Hkv,D)``, lse ``(Hq,Tq)`` fp32.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import dense
+from ..ops.merge import merge_partial
+from ..ops.plan import CPPlan, Segment
+from .comm import AllGatherComm, RingComm
+
+
+# ----------------------------------------------------------------------------------------------
+# per-source block execution (one ring step / one gathered slab)
+# ----------------------------------------------------------------------------------------------
+
+def _use_cuda_kernels(t: torch.Tensor) -> bool:
+    if not t.is_cuda:
+        return False
+    from ..ops import cuda_ext
+
+    return cuda_ext.available_for(t)
+
+
+def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out, lse):
+    """Fold the contribution of one source shard into the running (out, lse)."""
+    if not segs:
+        return out, lse
+    if _use_cuda_kernels(q):
+        from ..ops import attn_cuda
+
+        p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
+        return merge_partial(out, lse, p_out, p_lse)
+    if out is None:
+        out = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+        lse = torch.full((q.shape[1], q.shape[0]), float("-inf"), dtype=torch.float32, device=q.device)
+    for s in segs:
+        ch = plan.q_chunks[s.chunk]
+        rows = slice(ch.row0, ch.row0 + ch.rows)
+        kv = slice(s.kv_row0, s.kv_row0 + s.kv_len)
+        b_out, b_lse = dense.block_fwd(q[rows], k_src[kv], v_src[kv], scale, s.diag)
+        merge_partial(out, lse, b_out, b_lse, rows)
+    return out, lse
+
+
+def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse, delta, scale,
+                  dq, deterministic: bool = False):
+    """dq += (local); returns fp32 (dk, dv) of this source shard's rows (zeros where unseen)."""
+    dk = torch.zeros(k_src.shape, dtype=torch.float32, device=q.device)
+    dv = torch.zeros(v_src.shape, dtype=torch.float32, device=q.device)
+    if not segs:
+        return dk, dv
+    if _use_cuda_kernels(q):
+        from ..ops import attn_cuda
+
+        attn_cuda.segments_backward(plan, segs, dout, q, k_src, v_src, lse, delta, scale, dq, dk, dv,
+                                    deterministic)
+        return dk, dv
+    for s in segs:
+        ch = plan.q_chunks[s.chunk]
+        rows = slice(ch.row0, ch.row0 + ch.rows)
+        kv = slice(s.kv_row0, s.kv_row0 + s.kv_len)
+        b_dq, b_dk, b_dv = dense.block_bwd(dout[rows], q[rows], k_src[kv], v_src[kv], lse[:, rows],
+                                           delta[:, rows], scale, s.diag)
+        dq[rows] += b_dq
+        dk[kv] += b_dk
+        dv[kv] += b_dv
+    return dk, dv
+
+
+def _finish_forward(q, out, lse):
+    if out is None:  # nothing visible at all (cannot happen for valid plans, but stay total)
+        out = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+        lse = torch.full((q.shape[1], q.shape[0]), float("-inf"), dtype=torch.float32, device=q.device)
+    return out.to(q.dtype), lse
+
+
+def compute_delta(out: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    """delta[h, t] = sum_d out[t,h,d] * dout[t,h,d]  (fp32, (H,T))."""
+    return (out.float() * dout.float()).sum(-1).transpose(0, 1).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# ring transport (reference pattern: K/V hop to the next rank every step; dK/dV travel with them)
+# ----------------------------------------------------------------------------------------------
+
+def ring_forward(plan: CPPlan, q, k, v, scale, group) -> Tuple[torch.Tensor, torch.Tensor]:
+    comm = RingComm(group)
+    by_src = plan.by_src()
+    out = lse = None
+    cur_k, cur_v = k.contiguous(), v.contiguous()
+    for step in range(plan.world):
+        src = (plan.rank - step) % plan.world
+        last = step + 1 == plan.world
+        if not last:
+            nxt_k, nxt_v = comm.send_recv_kv(cur_k, cur_v)
+        out, lse = step_forward(plan, by_src.get(src, []), q, cur_k, cur_v, scale, out, lse)
+        if not last:
+            comm.wait()
+            cur_k, cur_v = nxt_k, nxt_v
+    return _finish_forward(q, out, lse)
+
+
+def ring_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, deterministic=False):
+    kv_comm, dkv_comm = RingComm(group), RingComm(group)
+    by_src = plan.by_src()
+    delta = compute_delta(out, dout)
+    dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    cur_k, cur_v = k.contiguous(), v.contiguous()
+    dk = dv = nxt_dk = nxt_dv = None
+    for step in range(plan.world):
+        src = (plan.rank - step) % plan.world
+        last = step + 1 == plan.world
+        if not last:
+            nxt_k, nxt_v = kv_comm.send_recv_kv(cur_k, cur_v)
+        b_dk, b_dv = step_backward(plan, by_src.get(src, []), dout, q, cur_k, cur_v, lse, delta, scale,
+                                   dq, deterministic)
+        if step == 0:
+            dk, dv = b_dk, b_dv
+        else:
+            dkv_comm.wait()  # accumulator of shard `src` arriving from the previous rank
+            dk, dv = nxt_dk + b_dk, nxt_dv + b_dv
+        if not last:
+            kv_comm.wait()
+            cur_k, cur_v = nxt_k, nxt_v
+        nxt_dk, nxt_dv = dkv_comm.send_recv_kv(dk, dv)
+    dkv_comm.wait()  # one extra hop brings every accumulator home
+    return dq.to(q.dtype), nxt_dk.to(k.dtype), nxt_dv.to(v.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# all-gather transport (llama3 pattern: gather a group of kv heads, attend, reduce-scatter grads)
+# ----------------------------------------------------------------------------------------------
+
+def _head_groups(hkv: int, stride: int):
+    if hkv % stride:
+        raise ValueError(f"heads_k_stride={stride} must divide the number of kv heads ({hkv})")
+    return range(0, hkv, stride)
+
+
+def _gather_heads(comm: AllGatherComm, k, v, h0, stride, buf):
+    comm.all_gather(buf[0], k[:, h0:h0 + stride].contiguous())
+    comm.all_gather(buf[1], v[:, h0:h0 + stride].contiguous())
+
+
+def allgather_forward(plan: CPPlan, q, k, v, scale, group, heads_k_stride: int):
+    W, L = plan.world, plan.kv_rows
+    hq, hkv, d = q.shape[1], k.shape[1], k.shape[2]
+    rep = hq // hkv
+    comm = AllGatherComm(group)
+    by_src = plan.by_src()
+    bufs = [torch.empty((2, W * L, heads_k_stride, d), dtype=k.dtype, device=k.device) for _ in range(2)]
+    out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    lse = torch.empty((hq, q.shape[0]), dtype=torch.float32, device=q.device)
+    groups = list(_head_groups(hkv, heads_k_stride))
+    _gather_heads(comm, k, v, groups[0], heads_k_stride, bufs[0])
+    for gi, h0 in enumerate(groups):
+        comm.wait()
+        cur = bufs[gi % 2]
+        if gi + 1 < len(groups):  # double buffering: next group's gather overlaps this group's math
+            _gather_heads(comm, k, v, groups[gi + 1], heads_k_stride, bufs[(gi + 1) % 2])
+        qs = slice(h0 * rep, (h0 + heads_k_stride) * rep)
+        q_g = q[:, qs]
+        o_g = l_g = None
+        for src in range(W):
+            o_g, l_g = step_forward(plan, by_src.get(src, []), q_g, cur[0, src * L:(src + 1) * L],
+                                    cur[1, src * L:(src + 1) * L], scale, o_g, l_g)
+        o_g, l_g = _finish_forward(q_g, o_g, l_g)
+        out[:, qs] = o_g
+        lse[qs] = l_g
+    return out, lse
+
+
+def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, heads_k_stride: int,
+                       deterministic=False):
+    W, L = plan.world, plan.kv_rows
+    hq, hkv, d = q.shape[1], k.shape[1], k.shape[2]
+    rep = hq // hkv
+    comm = AllGatherComm(group)
+    by_src = plan.by_src()
+    delta = compute_delta(out, dout)
+    bufs = [torch.empty((2, W * L, heads_k_stride, d), dtype=k.dtype, device=k.device) for _ in range(2)]
+    dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    dk = torch.empty(k.shape, dtype=k.dtype, device=k.device)
+    dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+    groups = list(_head_groups(hkv, heads_k_stride))
+    _gather_heads(comm, k, v, groups[0], heads_k_stride, bufs[0])
+    for gi, h0 in enumerate(groups):
+        comm.wait()
+        cur = bufs[gi % 2]
+        if gi + 1 < len(groups):
+            _gather_heads(comm, k, v, groups[gi + 1], heads_k_stride, bufs[(gi + 1) % 2])
+        qs = slice(h0 * rep, (h0 + heads_k_stride) * rep)
+        dq_g = torch.zeros(q[:, qs].shape, dtype=torch.float32, device=q.device)
+        dkv_full = torch.zeros((2, W * L, heads_k_stride, d), dtype=torch.float32, device=q.device)
+        for src in range(W):
+            sl = slice(src * L, (src + 1) * L)
+            b_dk, b_dv = step_backward(plan, by_src.get(src, []), dout[:, qs], q[:, qs], cur[0, sl],
+                                       cur[1, sl], lse[qs], delta[qs], scale, dq_g, deterministic)
+            dkv_full[0, sl] = b_dk
+            dkv_full[1, sl] = b_dv
+        dq[:, qs] = dq_g
+        if W > 1:
+            red = torch.empty((2, L, heads_k_stride, d), dtype=torch.float32, device=q.device)
+            dist.reduce_scatter_tensor(red[0], dkv_full[0], group=group)
+            dist.reduce_scatter_tensor(red[1], dkv_full[1], group=group)
+        else:
+            red = dkv_full
+        dk[:, h0:h0 + heads_k_stride] = red[0].to(k.dtype)
+        dv[:, h0:h0 + heads_k_stride] = red[1].to(v.dtype)
+    return dq.to(q.dtype), dk, dv
+
+
+# ----------------------------------------------------------------------------------------------
+# entry points used by the autograd bridge
+# ----------------------------------------------------------------------------------------------
+
+def _fused_ok(q: torch.Tensor, group) -> bool:
+    if not _use_cuda_kernels(q):
+        return False
+    from . import fused
+
+    return fused.available(q, group)
+
+
+def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_stride: int = 1):
+    if _fused_ok(q, group):
+        from . import fused
+
+        return fused.forward(plan, q, k, v, scale, group)
+    if transport == "allgather":
+        return allgather_forward(plan, q, k, v, scale, group, heads_k_stride)
+    return ring_forward(plan, q, k, v, scale, group)
+
+
+def cp_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, transport="ring",
+                heads_k_stride: int = 1, deterministic: bool = False):
+    if _fused_ok(q, group):
+        from . import fused
+
+        return fused.backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)
+    if transport == "allgather":
+        return allgather_backward(plan, dout, q, k, v, out, lse, scale, group, heads_k_stride, deterministic)
+    return ring_backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)

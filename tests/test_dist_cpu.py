@@ -1,0 +1,225 @@
+"""All public entry points on CPU/gloo (world_size 2 and 4) against the dense fp32 oracle.
+
+This is the reference's test strategy (/root/reference/test/test_*_func.py: full problem on every
+rank as oracle, per-rank shard comparison of out / lse / dq / dk / dv) with real tolerances, plus
+the coverage the reference lacks: kvpacked/unpacked entry points, GQA, non-causal, world sizes.
+"""
+import pytest
+import torch
+import torch.distributed as dist
+
+import ring_flash_attn_b200 as rfa
+from ring_flash_attn_b200.ops.dense import attention_oracle, varlen_attention_oracle
+from ring_flash_attn_b200.parallel import layouts
+from dist_utils import run_distributed
+
+TOL = dict(atol=2e-5, rtol=2e-4)
+
+
+def _bcast(t):
+    dist.broadcast(t, src=0)
+    return t
+
+
+def _batch_case(rank, world, scheme, causal, packing, hq, hkv, dtype):
+    torch.manual_seed(0)
+    b, d = 2, 16
+    s = 8 * world * 2
+    q = _bcast(torch.randn(b, s, hq, d, dtype=dtype))
+    k = _bcast(torch.randn(b, s, hkv, d, dtype=dtype))
+    v = _bcast(torch.randn(b, s, hkv, d, dtype=dtype))
+    dout = _bcast(torch.randn(b, s, hq, d, dtype=dtype))
+    shard = getattr(layouts, f"shard_{scheme}")
+    qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
+    ref_out, ref_lse = attention_oracle(qr, kr, vr, causal)
+    ref_out.backward(dout.float())
+
+    lq, lk, lv = (shard(x, rank, world).detach().requires_grad_(True) for x in (q, k, v))
+    prefix = {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}[scheme]
+    if packing == "qkv":
+        qkv = torch.stack([lq, lk, lv], dim=2).detach().requires_grad_(True)
+        fn = getattr(rfa, f"{prefix}_flash_attn_qkvpacked_func")
+        out, lse, _ = fn(qkv, causal=causal, return_attn_probs=True)
+    elif packing == "kv":
+        kv = torch.stack([lk, lv], dim=2).detach().requires_grad_(True)
+        fn = getattr(rfa, f"{prefix}_flash_attn_kvpacked_func")
+        out, lse, _ = fn(lq, kv, causal=causal, return_attn_probs=True)
+    else:
+        fn = getattr(rfa, f"{prefix}_flash_attn_func")
+        out, lse, _ = fn(lq, lk, lv, causal=causal, return_attn_probs=True)
+    assert out.dtype == dtype and lse.dtype == torch.float32
+    out.backward(shard(dout, rank, world))
+    if packing == "qkv":
+        gq, gk, gv = qkv.grad[:, :, 0], qkv.grad[:, :, 1], qkv.grad[:, :, 2]
+    elif packing == "kv":
+        gq, gk, gv = lq.grad, kv.grad[:, :, 0], kv.grad[:, :, 1]
+    else:
+        gq, gk, gv = lq.grad, lk.grad, lv.grad
+    tol = TOL if dtype == torch.float32 else dict(atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(out.float(), shard(ref_out, rank, world), **tol)
+    torch.testing.assert_close(lse, shard(ref_lse, rank, world, dim=2), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gq.float(), shard(qr.grad, rank, world).float(), **tol)
+    torch.testing.assert_close(gk.float(), shard(kr.grad, rank, world).float(), **tol)
+    torch.testing.assert_close(gv.float(), shard(vr.grad, rank, world).float(), **tol)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("scheme,causal,packing,hq,hkv", [
+    ("ring", True, "qkv", 4, 4), ("ring", False, "kv", 4, 2), ("ring", True, "none", 4, 1),
+    ("zigzag", True, "qkv", 4, 4), ("zigzag", True, "kv", 6, 2), ("zigzag", True, "none", 2, 2),
+    ("stripe", True, "qkv", 4, 4), ("stripe", True, "kv", 4, 2), ("stripe", True, "none", 3, 3),
+])
+def test_batch_schemes(world, scheme, causal, packing, hq, hkv):
+    run_distributed(_batch_case, world, scheme, causal, packing, hq, hkv, torch.float32)
+
+
+def test_batch_bf16_dtype_roundtrip():
+    run_distributed(_batch_case, 2, "zigzag", True, "qkv", 4, 4, torch.bfloat16)
+
+
+def test_baseline_config_1():
+    """BASELINE.json config 1: ring qkvpacked, world 2, bs=1 seq=256 nheads=4 d=64, fwd numerics."""
+    run_distributed(_config1, 2)
+
+
+def _config1(rank, world):
+    torch.manual_seed(1)
+    qkv = _bcast(torch.randn(1, 256, 3, 4, 64))
+    ref, ref_lse = attention_oracle(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], True)
+    out, lse, _ = rfa.ring_flash_attn_qkvpacked_func(layouts.shard_ring(qkv, rank, world), causal=True,
+                                                     return_attn_probs=True)
+    torch.testing.assert_close(out, layouts.shard_ring(ref, rank, world), **TOL)
+    torch.testing.assert_close(lse, layouts.shard_ring(ref_lse, rank, world, dim=2), atol=1e-4, rtol=1e-4)
+
+
+def _varlen_case(rank, world, scheme, causal, packing, hq, hkv):
+    torch.manual_seed(0)
+    d = 16
+    unit = 2 * world
+    lens = [unit * 2, unit * 5, unit * 3]
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    total = cu[-1]
+    q = _bcast(torch.randn(total, hq, d))
+    k = _bcast(torch.randn(total, hkv, d))
+    v = _bcast(torch.randn(total, hkv, d))
+    dout = _bcast(torch.randn(total, hq, d))
+    cu_t = torch.tensor(cu, dtype=torch.int32)
+    qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
+    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal)
+    ref_out.backward(dout)
+    shard = layouts.shard_ring_varlen if scheme == "ring" else layouts.shard_zigzag_varlen
+    lq, lk, lv = (shard(x, cu, rank, world).detach().requires_grad_(True) for x in (q, k, v))
+    local_cu = cu_t // world
+    max_s = int((local_cu[1:] - local_cu[:-1]).max())
+    prefix = "ring" if scheme == "ring" else "zigzag_ring"
+    if packing == "qkv":
+        qkv = torch.stack([lq, lk, lv], dim=1).detach().requires_grad_(True)
+        out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_varlen_qkvpacked_func")(
+            qkv, local_cu, max_s, causal=causal, return_attn_probs=True)
+    elif packing == "kv":
+        kv = torch.stack([lk, lv], dim=1).detach().requires_grad_(True)
+        out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_varlen_kvpacked_func")(
+            lq, kv, local_cu, max_s, causal=causal, return_attn_probs=True)
+    else:
+        out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_varlen_func")(
+            lq, lk, lv, local_cu, max_s, causal=causal, return_attn_probs=True)
+    out.backward(shard(dout, cu, rank, world))
+    if packing == "qkv":
+        gq, gk, gv = qkv.grad[:, 0], qkv.grad[:, 1], qkv.grad[:, 2]
+    elif packing == "kv":
+        gq, gk, gv = lq.grad, kv.grad[:, 0], kv.grad[:, 1]
+    else:
+        gq, gk, gv = lq.grad, lk.grad, lv.grad
+    torch.testing.assert_close(out, shard(ref_out, cu, rank, world), **TOL)
+    torch.testing.assert_close(lse, shard(ref_lse.transpose(0, 1), cu, rank, world).transpose(0, 1),
+                               atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gq, shard(qr.grad, cu, rank, world), **TOL)
+    torch.testing.assert_close(gk, shard(kr.grad, cu, rank, world), **TOL)
+    torch.testing.assert_close(gv, shard(vr.grad, cu, rank, world), **TOL)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("scheme,causal,packing,hq,hkv", [
+    ("ring", True, "qkv", 4, 4), ("ring", False, "kv", 4, 2), ("ring", True, "none", 2, 1),
+    ("zigzag", True, "qkv", 4, 4), ("zigzag", True, "kv", 4, 2), ("zigzag", True, "none", 2, 2),
+])
+def test_varlen_schemes(world, scheme, causal, packing, hq, hkv):
+    run_distributed(_varlen_case, world, scheme, causal, packing, hq, hkv)
+
+
+def _llama3_case(rank, world, causal, packing, hq, hkv, stride):
+    torch.manual_seed(0)
+    d = 8
+    cu = [0, 3 * world + 1, 7 * world - 1, 12 * world]
+    total = cu[-1]
+    q = _bcast(torch.randn(total, hq, d))
+    k = _bcast(torch.randn(total, hkv, d))
+    v = _bcast(torch.randn(total, hkv, d))
+    dout = _bcast(torch.randn(total, hq, d))
+    cu_t = torch.tensor(cu, dtype=torch.int32)
+    qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
+    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal)
+    ref_out.backward(dout)
+    sh = lambda x: layouts.shard_llama3(x, rank, world)  # noqa: E731
+    lq, lk, lv = (sh(x).detach().requires_grad_(True) for x in (q, k, v))
+    cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu_t, causal, rank, world)
+    if packing == "qkv":
+        qkv = torch.stack([lq, lk, lv], dim=1).detach().requires_grad_(True)
+        out, lse, _ = rfa.llama3_flash_attn_varlen_qkvpacked_func(
+            qkv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal, return_attn_probs=True)
+    elif packing == "kv":
+        kv = torch.stack([lk, lv], dim=1).detach().requires_grad_(True)
+        out, lse, _ = rfa.llama3_flash_attn_varlen_kvpacked_func(
+            lq, kv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal, return_attn_probs=True)
+    else:
+        out, lse, _ = rfa.llama3_flash_attn_varlen_func(
+            lq, lk, lv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal,
+            return_attn_probs=True)
+    out.backward(sh(dout))
+    if packing == "qkv":
+        gq, gk, gv = qkv.grad[:, 0], qkv.grad[:, 1], qkv.grad[:, 2]
+    elif packing == "kv":
+        gq, gk, gv = lq.grad, kv.grad[:, 0], kv.grad[:, 1]
+    else:
+        gq, gk, gv = lq.grad, lk.grad, lv.grad
+    torch.testing.assert_close(out, sh(ref_out), **TOL)
+    torch.testing.assert_close(lse, sh(ref_lse.transpose(0, 1)).transpose(0, 1), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gq, sh(qr.grad), **TOL)
+    torch.testing.assert_close(gk, sh(kr.grad), **TOL)
+    torch.testing.assert_close(gv, sh(vr.grad), **TOL)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("causal,packing,hq,hkv,stride", [
+    (True, "qkv", 4, 4, 1), (True, "kv", 4, 2, 2), (False, "none", 4, 2, 1), (True, "none", 8, 4, 4),
+])
+def test_llama3(world, causal, packing, hq, hkv, stride):
+    run_distributed(_llama3_case, world, causal, packing, hq, hkv, stride)
+
+
+def _single_process_case():
+    # world_size 1 without any process group: every scheme degenerates to plain attention
+    torch.manual_seed(0)
+    qkv = torch.randn(1, 32, 3, 2, 16, requires_grad=True)
+    ref, _ = attention_oracle(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], True)
+    for fn in (rfa.ring_flash_attn_qkvpacked_func, rfa.zigzag_ring_flash_attn_qkvpacked_func,
+               rfa.stripe_flash_attn_qkvpacked_func):
+        torch.testing.assert_close(fn(qkv, causal=True), ref, **TOL)
+
+
+def test_single_process_no_group():
+    _single_process_case()
+
+
+def test_argument_guards():
+    q = torch.randn(1, 8, 2, 16)
+    with pytest.raises(AssertionError):
+        rfa.zigzag_ring_flash_attn_func(q, q, q, causal=False)
+    with pytest.raises(AssertionError):
+        rfa.stripe_flash_attn_func(q, q, q, causal=False)
+    with pytest.raises(NotImplementedError):
+        rfa.ring_flash_attn_func(q, q, q, alibi_slopes=torch.ones(2))
+    with pytest.raises(NotImplementedError):
+        rfa.ring_flash_attn_func(q, q, q, dropout_p=0.1)
