@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Headline benchmark: zigzag ring flash attention, fwd+bwd iterations per second.
+
+Config (BASELINE.json "headline"): ``zigzag_ring_flash_attn_qkvpacked_func``, bf16, batch 1, 32 heads,
+head_dim 128, causal, 4096 tokens per GPU (sequence 32768 on 8 GPUs; weak scaling in tokens per GPU),
+synthetic random Q/K/V.  One step = forward + backward of the attention op through the public API.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config readme]
+
+``--impl reference`` runs the unmodified zhuzilin/ring-flash-attention installed in ``baseline/_ref``
+(flash_attn 2.8 + NCCL) on the same config and prints the same JSON line with ``"impl": "reference"``.
+``--config readme`` switches to the reference README's benchmark shape (8192 tokens per GPU, 32 query / 8 kv
+heads, kvpacked API), for which published H800 numbers exist.
+
+Timing: CUDA events around every step on the launching stream, an L2 flush (256 MiB write) between steps,
+barrier + synchronize on both sides of the timed region, max over ranks.  ``e2e`` repeats the measurement
+with the step's inputs copied from pinned host memory and the loss read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+PUBLISHED = {  # BASELINE.md, README config, fwd+bwd iter/s
+    ("readme", 8): 17.4,   # zigzag_ring, 8xH800
+    ("readme", 1): 154.7,  # flash_attn on the local 8K problem, 1xH800 (zigzag at world 1 is exactly this)
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="headline", choices=["headline", "readme"])
+    ap.add_argument("--mode", default="fwd_bwd", choices=["fwd_bwd", "fwd"])
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def unavailable(why: str):
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+    sys.exit(0)
+
+
+def load_reference():
+    """Import the UNMODIFIED reference from baseline/_ref.  Its package __init__ eagerly imports the HF
+    adapter, which does not import under transformers 5.x; a stub module object for that one submodule is
+    registered first so that the algorithm modules (the code path being benchmarked) load untouched."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "ring_flash_attn")):
+        unavailable("baseline/_ref/ring_flash_attn is not installed")
+    try:
+        import flash_attn  # noqa: F401
+    except Exception as e:  # noqa: BLE001
+        unavailable(f"flash_attn import failed: {type(e).__name__}: {e}")
+    sys.path.insert(0, ref_root)
+    import types
+
+    stub = types.ModuleType("ring_flash_attn.adapters")
+    stub.substitute_hf_flash_attn = None
+    stub.update_ring_flash_attn_params = None
+    sys.modules["ring_flash_attn.adapters"] = stub
+    try:
+        import ring_flash_attn
+    except Exception as e:  # noqa: BLE001
+        unavailable(f"reference import failed: {type(e).__name__}: {e}")
+    if not os.path.abspath(ring_flash_attn.__file__).startswith(os.path.abspath(ref_root)):
+        unavailable("ring_flash_attn resolved outside baseline/_ref")
+    return ring_flash_attn
+
+
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        if args.impl == "reference":
+            unavailable("no CUDA device")
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    need_pg = world > 1 or args.impl == "reference"
+    if need_pg and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29513")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    if args.config == "headline":
+        tokens, hq, hkv, api = 4096, 32, 32, "qkvpacked"
+    else:
+        tokens, hq, hkv, api = 8192, 32, 8, "kvpacked"
+    d = 128
+    dtype = torch.bfloat16
+
+    if args.impl == "reference":
+        mod = load_reference()
+    else:
+        sys.path.insert(0, ROOT)
+        import ring_flash_attn_b200 as mod
+    fn = getattr(mod, f"zigzag_ring_flash_attn_{api}_func")
+
+    torch.manual_seed(1234 + rank)
+    if api == "qkvpacked":
+        host_in = [torch.randn(1, tokens, 3, hq, d, dtype=dtype).pin_memory()]
+    else:
+        host_in = [torch.randn(1, tokens, hq, d, dtype=dtype).pin_memory(),
+                   torch.randn(1, tokens, 2, hkv, d, dtype=dtype).pin_memory()]
+    dev_in = [t.to(dev).requires_grad_(True) for t in host_in]
+    dout = torch.randn(1, tokens, hq, d, dtype=dtype, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_in)
+
+    def step(inputs):
+        if args.mode == "fwd":
+            with torch.no_grad():
+                return fn(*inputs, causal=True)
+        for t in inputs:
+            t.grad = None
+        out = fn(*inputs, causal=True)
+        out.backward(dout)
+        return out
+
+    def e2e_step():
+        ins = [h.to(dev, non_blocking=True).requires_grad_(args.mode != "fwd") for h in host_in]
+        out = step(ins)
+        loss_host.copy_(out.float().mean().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run, steps, warmup):
+        for _ in range(warmup):
+            run()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations (outside the events)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    launches = None
+    if args.impl == "ours":
+        from ring_flash_attn_b200.ops import cuda_ext
+
+        counter = cuda_ext.launch_counter()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    warm = max(args.warmup, 3)
+    # warm up once before counting launches
+    ms = None
+    for _ in range(warm):
+        step(dev_in)
+    if args.impl == "ours":
+        counter.reset()
+    ms = timed(lambda: step(dev_in), args.steps, 0)
+    if args.impl == "ours":
+        launches = counter.value
+    e2e = None
+    if not args.no_e2e:
+        e2e_ms = timed(e2e_step, args.steps, warm)
+        e2e = {"value": 1000.0 / e2e_ms, "unit": "iter/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        value = 1000.0 / ms
+        # causal attention FLOPs of the whole job: fwd 4*S^2*H*D/2, bwd 2.5x
+        S = tokens * world
+        fwd_flops = 2.0 * S * S * hq * d
+        flops = fwd_flops * (3.5 if args.mode == "fwd_bwd" else 1.0)
+        pub = PUBLISHED.get((args.config, world)) if args.mode == "fwd_bwd" else None
+        line = {
+            "metric": f"zigzag_ring_flash_attn_{api}_func {args.mode} iter/s",
+            "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / pub) if pub else None, "dtype": "bf16", "data": "synthetic",
+            "impl": args.impl,
+            "config": {"model": "attention op (Llama-style heads)", "global_batch": 1, "seq_len": S,
+                       "tokens_per_gpu": tokens, "nheads_q": hq, "nheads_kv": hkv, "head_dim": d, "causal": True,
+                       "parallelism": f"cp{world}-zigzag", "api": f"zigzag_ring_flash_attn_{api}_func",
+                       "name": args.config, "l2": "flushed with a 256 MiB write between timed steps"},
+            "tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12,
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if launches is not None:
+            line["gpu_launches"] = launches
+        print(json.dumps(line))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,535 @@
+// Blockwise flash-attention backward for sm_100a (head_dim 128, bf16/fp16).
+//
+// One CTA = one 128-key tile of one kv head.  dK and dV of that tile stay in tensor memory while the CTA
+// sweeps every query tile (64 rows) of every query head of the GQA group and every query segment that can
+// see the keys; dQ tiles are produced transposed, staged through shared memory and added into an fp32
+// accumulator with TMA reduce-add.  This replaces flash_attn's backward + the reference's fp32
+// dq/dk/dv bookkeeping per ring step (/root/reference/ring_flash_attn/ring_flash_attn.py:97-152).
+//
+// Per query tile i (all GEMMs on tcgen05, accumulators in TMEM):
+//   S^T  = K  Q_i^T        (128 keys x 64 queries)        SS, both K-major
+//   dP^T = V  dO_i^T                                      SS, both K-major
+//   P^T  = exp2(S^T * c - lse_i)          -> TMEM (bf16), dS^T = P^T o (dP^T - delta_i) * scale -> smem
+//   dV  += P^T  dO_i       (A from TMEM, B = dO MN-major)
+//   dK  += dS^T Q_i        (A = dS^T smem K-major, B = Q MN-major)
+//   dQ_i^T = K^T dS_i      (A = K MN-major, B = dS^T MN-major)  -> fp32 smem -> TMA reduce-add
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 softmax (thread == key row), warps 8-11 dQ drain (thread == head-dim lane).
+// TMEM (512 columns): S^T x2 [0,128)  dP^T [128,192)  dQ^T [192,256)  dV [256,384)  dK [384,512).
+#include <math_constants.h>
+#include <stdio.h>
+
+#include "attn_common.h"
+#include "sm100_ptx.cuh"
+
+namespace rfa {
+namespace bwd {
+
+constexpr int kD = 128;
+constexpr int kTileK = 128;  // keys per CTA
+constexpr int kTileQ = 64;   // queries per inner iteration
+constexpr int kStages = 3;   // Q/dO ring
+constexpr int kThreads = 384;
+constexpr int kKVBytes = kTileK * kD * 2;          // 32 KB each for K and V
+constexpr int kQBytes = kTileQ * kD * 2;           // 16 KB each for Q and dO
+constexpr int kQHalf = kQBytes / 2;                // 64-wide swizzled sub-tile of a 64-row tile (8 KB)
+constexpr int kKVHalf = kKVBytes / 2;              // 16 KB
+constexpr int kDSBytes = kTileK * kTileQ * 2;      // 16 KB
+constexpr int kDQBytes = kTileQ * kD * 4;          // 32 KB fp32 staging
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 192, kColDV = 256, kColDK = 384;
+
+struct Barriers {
+  uint64_t kv_full;
+  uint64_t qdo_full[kStages];
+  uint64_t qdo_empty[kStages];
+  uint64_t stat_full[kStages];
+  uint64_t s_full[2];
+  uint64_t p_ready;
+  uint64_t dp_full;
+  uint64_t ds_ready;
+  uint64_t dq_full;
+  uint64_t dq_free;
+  uint64_t dkv_done;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+constexpr int kStatBytes = kStages * 2 * kTileQ * 4;  // lse / delta ring, same slots as Q/dO
+constexpr int kSmemBytes =
+    2 * kKVBytes + kStages * 2 * kQBytes + kDSBytes + kDQBytes + kStatBytes + 1024 /*barriers*/ + 1024 /*slack*/;
+
+// Query tiles of one segment that can see this key tile.
+struct QGeom {
+  int q_row0, q_len, diag;
+  int t_begin, t_end;  // 64-row tile range
+};
+__device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
+  QGeom g;
+  g.q_row0 = s.q_row0;
+  g.q_len = s.q_len;
+  g.diag = s.diag;
+  const int first = s.diag >= 0 ? 0 : -s.diag;  // first chunk row that sees key 0 of the tile
+  g.t_begin = first / kTileQ;
+  g.t_end = (s.q_len + kTileQ - 1) / kTileQ;
+  if (g.t_begin > g.t_end) g.t_begin = g.t_end;
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_k = smem;
+  uint8_t* smem_v = smem_k + kKVBytes;
+  uint8_t* smem_qdo = smem_v + kKVBytes;                 // kStages x (Q 16 KB, dO 16 KB)
+  uint8_t* smem_ds = smem_qdo + kStages * 2 * kQBytes;   // 16 KB, [128 keys][64 queries] swizzled
+  float* smem_dq = reinterpret_cast<float*>(smem_ds + kDSBytes);   // [64 queries][128 dims] fp32
+  float* smem_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem_dq) + kDQBytes);  // [2][2][64]
+  Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(smem_stat) + kStatBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kv_head = blockIdx.y;
+  const int group = p.hq / p.hkv;
+  const BwdItem it = p.items[blockIdx.x];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_dq);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->kv_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->qdo_full[i], 1);
+      mbar_init(&bars->qdo_empty[i], 1);
+      mbar_init(&bars->stat_full[i], 1);
+    }
+    mbar_init(&bars->s_full[0], 1);
+    mbar_init(&bars->s_full[1], 1);
+    mbar_init(&bars->p_ready, 128);
+    mbar_init(&bars->dp_full, 1);
+    mbar_init(&bars->ds_ready, 128);
+    mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_free, 128);
+    mbar_init(&bars->dkv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  // total number of query tiles this CTA sweeps (identical in every role)
+  int tiles_per_head = 0;
+  for (int si = 0; si < it.seg_count; ++si) {
+    const QGeom g = q_geom(p.qsegs[it.seg_begin + si]);
+    tiles_per_head += g.t_end - g.t_begin;
+  }
+  const int total_tiles = tiles_per_head * group;
+
+  if (warp < 4) {
+    reg_dealloc<80>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        if (it.flag >= 0 && p.ready_flags != nullptr) {
+          wait_flag_ge(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready");
+          fence_proxy_async_all();
+        }
+        mbar_arrive_expect_tx(&bars->kv_full, 2 * kKVBytes);
+        tma_load_3d(smem_k, &tm_k, &bars->kv_full, 0, kv_head, it.kv_row0);
+        tma_load_3d(smem_k + kKVHalf, &tm_k, &bars->kv_full, 64, kv_head, it.kv_row0);
+        tma_load_3d(smem_v, &tm_v, &bars->kv_full, 0, kv_head, it.kv_row0);
+        tma_load_3d(smem_v + kKVHalf, &tm_v, &bars->kv_full, 64, kv_head, it.kv_row0);
+        uint32_t slot = 0, phase = 0;
+        for (int gq = 0; gq < group; ++gq) {
+          const int head = kv_head * group + gq;
+          for (int si = 0; si < it.seg_count; ++si) {
+            const QGeom g = q_geom(p.qsegs[it.seg_begin + si]);
+            for (int ti = g.t_begin; ti < g.t_end; ++ti) {
+              const int row = g.q_row0 + ti * kTileQ;
+              mbar_wait(&bars->qdo_empty[slot], phase ^ 1);
+              uint8_t* dq_ = smem_qdo + slot * 2 * kQBytes;
+              uint8_t* ddo = dq_ + kQBytes;
+              mbar_arrive_expect_tx(&bars->qdo_full[slot], 2 * kQBytes);
+              tma_load_3d(dq_, &tm_q, &bars->qdo_full[slot], 0, head, row);
+              tma_load_3d(dq_ + kQHalf, &tm_q, &bars->qdo_full[slot], 64, head, row);
+              tma_load_3d(ddo, &tm_do, &bars->qdo_full[slot], 0, head, row);
+              tma_load_3d(ddo + kQHalf, &tm_do, &bars->qdo_full[slot], 64, head, row);
+              if (++slot == kStages) {
+                slot = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
+      if (lane == 0 && total_tiles > 0) {
+        constexpr uint32_t fmt = Pack2<T>::kFmt;
+        constexpr uint32_t idesc_st = umma_idesc_f16(fmt, kTileK, kTileQ, 0, 0);  // S^T, dP^T
+        constexpr uint32_t idesc_dv = umma_idesc_f16(fmt, kTileK, kD, 0, 1);      // dV (A tmem), dK (A smem)
+        constexpr uint32_t idesc_dq = umma_idesc_f16(fmt, kD, kTileQ, 1, 1);      // dQ^T
+        const uint32_t k_base = smem_u32(smem_k), v_base = smem_u32(smem_v);
+        const uint32_t qdo_base = smem_u32(smem_qdo), ds_base = smem_u32(smem_ds);
+
+        // S^T / dP^T: A = K or V tile (128 rows, K-major), B = Q or dO tile (64 rows, K-major)
+        auto issue_kq = [&](uint32_t d_col, uint32_t a_base, uint32_t b_base) {
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) {
+            const uint32_t a = a_base + (k >> 2) * kKVHalf + (k & 3) * 32;
+            const uint32_t b = b_base + (k >> 2) * kQHalf + (k & 3) * 32;
+            umma_ss(d_col, umma_smem_desc(a, 16, 1024, kSwizzle128B), umma_smem_desc(b, 16, 1024, kSwizzle128B),
+                    idesc_st, k > 0);
+          }
+        };
+        // B = [64 rows][128 dims] tile read MN-major (N = dims): LBO = 8 KB between the two 64-dim halves,
+        // SBO = 1 KB between 8-row groups, 16 rows (2 KB) per MMA.
+        auto qdo_mn_desc = [&](uint32_t base, int k) {
+          return umma_smem_desc(base + k * 2048, kQHalf, 1024, kSwizzle128B);
+        };
+
+        mbar_wait(&bars->kv_full, 0);
+        tc_fence_after();
+
+        uint32_t slot = 0, phase = 0;
+        uint32_t ph_p = 0, ph_ds = 0, ph_dqfree = 0;
+        // software pipeline: S^T of tile i+1 is issued before the dV/dK/dQ GEMMs of tile i
+        int issued_s = 0;          // tiles whose S^T has been issued
+        uint32_t s_slot = 0, s_phase = 0;  // ring position used by the next S^T issue
+        auto issue_s = [&]() {
+          mbar_wait(&bars->qdo_full[s_slot], s_phase);
+          tc_fence_after();
+          const uint32_t qb = qdo_base + s_slot * 2 * kQBytes;
+          issue_kq(tmem + kColS + (issued_s & 1) * 64, k_base, qb);
+          umma_commit(&bars->s_full[issued_s & 1]);
+          ++issued_s;
+          if (++s_slot == kStages) {
+            s_slot = 0;
+            s_phase ^= 1;
+          }
+        };
+        issue_s();
+        // dP^T of tile 0
+        issue_kq(tmem + kColDP, v_base, qdo_base + kQBytes);
+        umma_commit(&bars->dp_full);
+        for (int i = 0; i < total_tiles; ++i) {
+          const uint32_t qb = qdo_base + slot * 2 * kQBytes;
+          const uint32_t dob = qb + kQBytes;
+          if (i + 1 < total_tiles) issue_s();
+          // dV += P^T dO   (P^T: bf16 in the first 32 columns of this tile's S^T buffer)
+          mbar_wait(&bars->p_ready, ph_p);
+          ph_p ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kTileQ / 16; ++k)
+            umma_ts(tmem + kColDV, tmem + kColS + (i & 1) * 64 + k * 8, qdo_mn_desc(dob, k), idesc_dv,
+                    (i > 0 || k > 0) ? 1u : 0u);
+          // dK += dS^T Q ; dQ^T = K^T dS
+          mbar_wait(&bars->ds_ready, ph_ds);
+          ph_ds ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kTileQ / 16; ++k)
+            umma_ss(tmem + kColDK, umma_smem_desc(ds_base + k * 32, 16, 1024, kSwizzle128B), qdo_mn_desc(qb, k),
+                    idesc_dv, (i > 0 || k > 0) ? 1u : 0u);
+          if (i > 0) {  // previous dQ^T must have been drained out of TMEM
+            mbar_wait(&bars->dq_free, ph_dqfree);
+            ph_dqfree ^= 1;
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k)
+            umma_ss(tmem + kColDQ, umma_smem_desc(k_base + k * 2048, kKVHalf, 1024, kSwizzle128B),
+                    umma_smem_desc(ds_base + k * 2048, 16, 1024, kSwizzle128B), idesc_dq, k > 0);
+          umma_commit(&bars->dq_full);
+          umma_commit(&bars->qdo_empty[slot]);  // Q_i / dO_i no longer needed once everything above retires
+          if (++slot == kStages) {
+            slot = 0;
+            phase ^= 1;
+          }
+          // dP^T of the next tile (its dO stage is `slot` now); the softmax warps have finished reading the
+          // previous dP^T because ds_ready was observed above.
+          if (i + 1 < total_tiles) {
+            mbar_wait(&bars->qdo_full[slot], phase);  // already landed (S^T of that tile was issued)
+            tc_fence_after();
+            issue_kq(tmem + kColDP, v_base, qdo_base + slot * 2 * kQBytes + kQBytes);
+            umma_commit(&bars->dp_full);
+          }
+        }
+        umma_commit(&bars->dkv_done);
+      }
+    } else if (warp == 3) {
+      // ---------------------------------------------------------------- per-query statistics producer
+      // lse (converted to log2 units; +inf for rows that do not exist or saw no key => P = 0) and delta.
+      uint32_t slot = 0, phase = 0;
+      for (int gq = 0; gq < group; ++gq) {
+        const int head = kv_head * group + gq;
+        for (int si = 0; si < it.seg_count; ++si) {
+          const QGeom g = q_geom(p.qsegs[it.seg_begin + si]);
+          for (int ti = g.t_begin; ti < g.t_end; ++ti) {
+            float l2[2], dl[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int qi = ti * kTileQ + lane + 32 * h;
+              l2[h] = CUDART_INF_F;
+              dl[h] = 0.f;
+              if (qi < g.q_len) {
+                const int row = g.q_row0 + qi;
+                const size_t b = row / p.lse_S, sidx = row % p.lse_S;
+                const size_t idx = (b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx;
+                const float x = p.lse[idx];
+                l2[h] = x == -CUDART_INF_F ? CUDART_INF_F : x * 1.4426950408889634f;
+                dl[h] = p.delta[idx];
+              }
+            }
+            mbar_wait(&bars->qdo_empty[slot], phase ^ 1);
+            float* st = smem_stat + slot * 2 * kTileQ;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              st[lane + 32 * h] = l2[h];
+              st[kTileQ + lane + 32 * h] = dl[h];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->stat_full[slot]);
+            if (++slot == kStages) {
+              slot = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ softmax warpgroup (thread == key row)
+    reg_alloc<216>();
+    const int wg_tid = threadIdx.x - 128;
+    const int key = wg_tid;                       // row in the key tile
+    const bool key_ok = key < it.kv_rows;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t ph_s[2] = {0, 0};
+    uint32_t ph_dp = 0;
+    uint32_t st_slot = 0, st_phase = 0;
+    int i = 0;
+    for (int gq = 0; gq < group; ++gq) {
+      for (int si = 0; si < it.seg_count; ++si) {
+        const QGeom g = q_geom(p.qsegs[it.seg_begin + si]);
+        for (int ti = g.t_begin; ti < g.t_end; ++ti, ++i) {
+          const float* st = smem_stat + st_slot * 2 * kTileQ;
+          mbar_wait(&bars->stat_full[st_slot], st_phase);
+          if (++st_slot == kStages) {
+            st_slot = 0;
+            st_phase ^= 1;
+          }
+
+          const int buf = i & 1;
+          const uint32_t t_s = tmem + kColS + buf * 64 + lane_addr;
+          mbar_wait(&bars->s_full[buf], ph_s[buf]);
+          ph_s[buf] ^= 1;
+          tc_fence_after();
+          uint32_t sr[64];
+          tmem_ld32(t_s, sr);
+          tmem_ld32(t_s + 32, sr + 32);
+          tmem_ld_wait();
+          // causal boundary: key visible to query qi iff key <= qi + diag  <=>  qi >= key - diag
+          const long long first_q = static_cast<long long>(key) - g.diag - static_cast<long long>(ti) * kTileQ;
+          const int q_lo = !key_ok ? kTileQ : (first_q < 0 ? 0 : (first_q > kTileQ ? kTileQ : static_cast<int>(first_q)));
+          float pr[64];
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float e = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -st[c]));
+            pr[c] = c >= q_lo ? e : 0.f;
+          }
+          {
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) pk[c] = Pack2<T>::pack(pr[2 * c], pr[2 * c + 1]);
+            tmem_st32(t_s, pk);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->p_ready);
+
+          // dS^T = P^T o (dP^T - delta) * scale  -> shared memory, 128-byte swizzled rows of 64 bf16
+          mbar_wait(&bars->dp_full, ph_dp);
+          ph_dp ^= 1;
+          tc_fence_after();
+          uint32_t dpr[64];
+          tmem_ld32(tmem + kColDP + lane_addr, dpr);
+          tmem_ld32(tmem + kColDP + lane_addr + 32, dpr + 32);
+          tmem_ld_wait();
+          uint8_t* ds_row = smem_ds + key * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 v;
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = ch * 8 + e * 2;
+              const float d0 = pr[c] * (__uint_as_float(dpr[c]) - st[kTileQ + c]) * p.scale;
+              const float d1 = pr[c + 1] * (__uint_as_float(dpr[c + 1]) - st[kTileQ + c + 1]) * p.scale;
+              w[e] = Pack2<T>::pack(d0, d1);
+            }
+            v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
+            *reinterpret_cast<uint4*>(ds_row + ((ch ^ (key & 7)) << 4)) = v;
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&bars->ds_ready);
+        }
+      }
+    }
+    // ---------------------------------------------------------------- epilogue: dK / dV tile -> global (fp32)
+    const int row = it.kv_row0 + key;
+    if (total_tiles > 0) {
+      mbar_wait(&bars->dkv_done, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      float* dst = (which == 0 ? p.dk : p.dv) + (static_cast<size_t>(row) * p.hkv + kv_head) * kD;
+      const uint32_t col = tmem + (which == 0 ? kColDK : kColDV) + lane_addr;
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        if (total_tiles > 0) {
+          tmem_ld32(col + c, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = 0;
+        }
+        if (key_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<uint4*>(dst + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ dQ drain warpgroup (thread == dim)
+    reg_alloc<216>();
+    const int wg_tid = threadIdx.x - 256;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t ph = 0;
+    int i = 0;
+    for (int gq = 0; gq < group; ++gq) {
+      const int head = kv_head * group + gq;
+      for (int si = 0; si < it.seg_count; ++si) {
+        const QGeom g = q_geom(p.qsegs[it.seg_begin + si]);
+        for (int ti = g.t_begin; ti < g.t_end; ++ti, ++i) {
+          mbar_wait(&bars->dq_full, ph);
+          ph ^= 1;
+          tc_fence_after();
+          uint32_t r[64];
+          tmem_ld32(tmem + kColDQ + lane_addr, r);
+          tmem_ld32(tmem + kColDQ + lane_addr + 32, r + 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->dq_free);
+          // the previous tile's reduce must have finished reading the staging buffer
+          if (wg_tid == 0) tma_store_wait_read<0>();
+          named_bar_sync(2, 128);
+#pragma unroll
+          for (int q = 0; q < kTileQ; ++q) smem_dq[q * kD + wg_tid] = __uint_as_float(r[q]);
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (wg_tid == 0) {
+            tma_reduce_add_3d(&tm_dq, smem_dq, 0, head, g.q_row0 + ti * kTileQ);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (wg_tid == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+}
+
+// delta[h, t] = sum_d out[t,h,d] * dout[t,h,d]; one warp per (row, head).
+template <typename T>
+__global__ void bwd_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
+                                 int rows, int hq, int lse_S, int64_t o_rs, int64_t o_hs, int64_t do_rs,
+                                 int64_t do_hs) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= rows * hq) return;
+  const int row = gw / hq, head = gw % hq;
+  const uint2 a = *reinterpret_cast<const uint2*>(out + row * o_rs + head * o_hs + lane * 4);
+  const uint2 b = *reinterpret_cast<const uint2*>(dout + row * do_rs + head * do_hs + lane * 4);
+  const T* pa = reinterpret_cast<const T*>(&a);
+  const T* pb = reinterpret_cast<const T*>(&b);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += static_cast<float>(pa[i]) * static_cast<float>(pb[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const size_t b_ = row / lse_S, sidx = row % lse_S;
+    delta[(b_ * hq + head) * static_cast<size_t>(lse_S) + sidx] = s;
+  }
+}
+
+}  // namespace bwd
+
+const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const TensorView& dout, float* delta, int lse_S,
+                                  cudaStream_t stream) {
+  const int rows = static_cast<int>(out.rows), hq = out.heads;
+  const long long warps = static_cast<long long>(rows) * hq;
+  if (warps == 0) return nullptr;
+  const int threads = 256;
+  const int blocks = static_cast<int>((warps * 32 + threads - 1) / threads);
+  if (dtype == kDtypeBF16) {
+    bwd::bwd_delta_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(out.ptr), static_cast<const __nv_bfloat16*>(dout.ptr), delta, rows, hq, lse_S,
+        out.row_stride, out.head_stride, dout.row_stride, dout.head_stride);
+  } else {
+    bwd::bwd_delta_kernel<__half><<<blocks, threads, 0, stream>>>(
+        static_cast<const __half*>(out.ptr), static_cast<const __half*>(dout.ptr), delta, rows, hq, lse_S,
+        out.row_stride, out.head_stride, dout.row_stride, dout.head_stride);
+  }
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& dout, const TensorView& k,
+                            const TensorView& v, const TensorView& dq_accum, const BwdParams& p, int n_items,
+                            cudaStream_t stream) {
+  if (n_items <= 0) return nullptr;
+  CUtensorMap tq, tdo, tk, tv, tdq;
+  if (const char* e = make_tensor_map(&tq, q, 2, bwd::kTileQ, bwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tdo, dout, 2, bwd::kTileQ, bwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tk, k, 2, bwd::kTileK, bwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tv, v, 2, bwd::kTileK, bwd::kD)) return e;
+  if (const char* e = make_plain_tensor_map(&tdq, dq_accum, 4, bwd::kTileQ, bwd::kD)) return e;
+  dim3 grid(n_items, p.hkv, 1), block(bwd::kThreads, 1, 1);
+  cudaError_t err;
+  if (dtype == kDtypeBF16) {
+    auto kern = bwd::attn_bwd_kernel<__nv_bfloat16>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+    if (err != cudaSuccess) return cudaGetErrorString(err);
+    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tdq, p);
+  } else {
+    auto kern = bwd::attn_bwd_kernel<__half>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+    if (err != cudaSuccess) return cudaGetErrorString(err);
+    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tdq, p);
+  }
+  err = cudaGetLastError();
+  return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+}  // namespace rfa

@@ -1,0 +1,426 @@
+// Blockwise flash-attention forward for sm_100a (head_dim 128, bf16/fp16).
+//
+// One CTA = one work item (<= 256 query rows of one chunk = two 128-row MMA tiles) x one query head.
+// The CTA walks a *segment list*: runs of keys - possibly from several source ranks - each with its own
+// causal diagonal.  The output accumulator never leaves tensor memory between segments, so a whole
+// ring / zigzag / stripe / llama3 forward is ordinary online softmax over the concatenated segments
+// (this replaces the reference's flash_attn call + fp32 out/lse merge per ring step,
+// /root/reference/ring_flash_attn/ring_flash_attn.py:26-63 and utils.py:32-73).
+//
+// Warp roles (384 threads):
+//   warp 0      TMA producer: Q tiles once, then K / V tiles through a ring of 32 KB stages
+//   warp 1      tcgen05.mma issuer: S_t = Q_t K^T (SS), O_t += P_t V (P from TMEM, V MN-major from smem)
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax warpgroup for tile 0 (thread == row): S -> regs, mask, max, exp2, P -> TMEM,
+//               lazy O rescale, final normalisation + store of out / lse
+//   warps 8-11  the same for tile 1
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t aliases the first 64
+// columns of S_t.  The MMA warp ping-pongs the two tiles so one tile's softmax overlaps the other's MMAs.
+#include <math_constants.h>
+#include <stdio.h>
+
+#include "attn_common.h"
+#include "sm100_ptx.cuh"
+
+namespace rfa {
+
+namespace fwd {
+
+constexpr int kD = 128;             // head dim
+constexpr int kTile = 128;          // rows per MMA tile (queries and keys)
+constexpr int kStages = 4;          // K/V ring slots
+constexpr int kTileBytes = kTile * kD * 2;  // 32 KB
+constexpr int kHalfBytes = kTileBytes / 2;  // one 64-element-wide swizzled sub-tile
+constexpr int kThreads = 384;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays below 2^8
+
+struct Barriers {
+  uint64_t q_full[2];
+  uint64_t kv_full[kStages];
+  uint64_t kv_empty[kStages];
+  uint64_t s_full[2];
+  uint64_t p_ready[2];
+  uint64_t o_done[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+
+// Per-(item, segment) geometry shared by all roles so that they agree on the iteration space.
+struct SegGeom {
+  int kv_row0, kv_len, diag;
+  int n_tiles;  // key tiles to visit
+};
+
+__device__ __forceinline__ SegGeom seg_geom(const KVSegment& s, const WorkItem& it) {
+  SegGeom g;
+  g.kv_row0 = s.kv_row0;
+  g.kv_len = s.kv_len;
+  g.diag = s.diag;
+  const int last_row = it.q_off + it.q_rows - 1;
+  long long lim = static_cast<long long>(last_row) + s.diag + 1;  // keys [0, lim) reachable by the last row
+  int reach = lim < 0 ? 0 : (lim > s.kv_len ? s.kv_len : static_cast<int>(lim));
+  g.n_tiles = (reach + kTile - 1) / kTile;
+  return g;
+}
+// Is tile t (rows [q_off + 128 t, ...)) touching key tile jj at all?
+__device__ __forceinline__ bool tile_active(const SegGeom& g, const WorkItem& it, int t, int jj) {
+  const int n_t = t == 0 ? (it.q_rows < kTile ? it.q_rows : kTile) : it.q_rows - kTile;
+  if (n_t <= 0) return false;
+  const int last_row = it.q_off + t * kTile + n_t - 1;
+  return static_cast<long long>(jj) * kTile <= static_cast<long long>(last_row) + g.diag;
+}
+__device__ __forceinline__ bool tile_needs_mask(const SegGeom& g, const WorkItem& it, int t, int jj) {
+  const int first_row = it.q_off + t * kTile;
+  const bool ragged = (jj + 1) * kTile > g.kv_len;
+  const bool diagonal = static_cast<long long>(jj) * kTile + (kTile - 1) > static_cast<long long>(first_row) + g.diag;
+  return ragged || diagonal;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                       // 2 x 32 KB
+  uint8_t* smem_kv = smem + 2 * kTileBytes;     // kStages x 32 KB
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_kv + kStages * kTileBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int kv_head = head / (p.hq / p.hkv);
+  const WorkItem it = p.items[blockIdx.x];
+  const int n_rows0 = it.q_rows < kTile ? it.q_rows : kTile;
+  const int n_rows1 = it.q_rows - n_rows0;
+  const bool has_t1 = n_rows1 > 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_ready[i], 128);
+      mbar_init(&bars->o_done[i], 1);
+    }
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  if (warp < 4) {
+   reg_dealloc<80>();
+   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->q_full[0], kTileBytes);
+      tma_load_3d(smem_q, &tm_q, &bars->q_full[0], 0, head, it.q_row0);
+      tma_load_3d(smem_q + kHalfBytes, &tm_q, &bars->q_full[0], 64, head, it.q_row0);
+      if (has_t1) {
+        mbar_arrive_expect_tx(&bars->q_full[1], kTileBytes);
+        tma_load_3d(smem_q + kTileBytes, &tm_q, &bars->q_full[1], 0, head, it.q_row0 + kTile);
+        tma_load_3d(smem_q + kTileBytes + kHalfBytes, &tm_q, &bars->q_full[1], 64, head, it.q_row0 + kTile);
+      }
+      uint32_t slot = 0, phase = 0;
+      for (int si = 0; si < it.seg_count; ++si) {
+        const KVSegment sg = p.segs[it.seg_begin + si];
+        const SegGeom g = seg_geom(sg, it);
+        if (g.n_tiles > 0 && sg.flag >= 0 && p.ready_flags != nullptr) {
+          wait_flag_ge(p.ready_flags + sg.flag, p.ready_epoch, "fwd kv ready");
+          fence_proxy_async_all();
+        }
+        for (int jj = 0; jj < g.n_tiles; ++jj) {
+          const int row = g.kv_row0 + jj * kTile;
+          for (int kv = 0; kv < 2; ++kv) {
+            mbar_wait(&bars->kv_empty[slot], phase ^ 1);
+            uint8_t* dst = smem_kv + slot * kTileBytes;
+            const CUtensorMap* tm = kv == 0 ? &tm_k : &tm_v;
+            mbar_arrive_expect_tx(&bars->kv_full[slot], kTileBytes);
+            tma_load_3d(dst, tm, &bars->kv_full[slot], 0, kv_head, row);
+            tma_load_3d(dst + kHalfBytes, tm, &bars->kv_full[slot], 64, kv_head, row);
+            if (++slot == kStages) {
+              slot = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(Pack2<T>::kFmt, kTile, kTile, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(Pack2<T>::kFmt, kTile, kD, 0, 1);
+      const uint32_t q_base = smem_u32(smem_q);
+      const uint32_t kv_base = smem_u32(smem_kv);
+      const uint32_t col_s[2] = {tmem + kColS0, tmem + kColS1};
+      const uint32_t col_o[2] = {tmem + kColO0, tmem + kColO1};
+
+      auto issue_qk = [&](int t, uint32_t k_slot) {
+        const uint32_t qa = q_base + t * kTileBytes;
+        const uint32_t kb = kv_base + k_slot * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+          umma_ss(col_s[t], umma_smem_desc(qa + off, 16, 1024, kSwizzle128B),
+                  umma_smem_desc(kb + off, 16, 1024, kSwizzle128B), idesc_qk, k > 0);
+        }
+        umma_commit(&bars->s_full[t]);
+      };
+      auto issue_pv = [&](int t, uint32_t v_slot, bool accumulate) {
+        const uint32_t vb = kv_base + v_slot * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          // V tile is [128 keys][2 x 64 dims] -> MN-major B: LBO = stride between the two 64-wide halves,
+          // SBO = stride between 8-key groups; one MMA consumes 16 keys = 2048 bytes.
+          umma_ts(col_o[t], col_s[t] + k * 8, umma_smem_desc(vb + k * 2048, kHalfBytes, 1024, kSwizzle128B),
+                  idesc_pv, (accumulate || k > 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(&bars->q_full[0], 0);
+      if (has_t1) mbar_wait(&bars->q_full[1], 0);
+      tc_fence_after();
+
+      uint32_t slot = 0, phase = 0;            // ring position of the next K tile
+      uint32_t p_phase[2] = {0, 0};
+      bool o_started[2] = {false, false};
+      bool pend1 = false;                      // PV of tile 1 deferred to the next iteration
+      uint32_t pend1_slot = 0;
+      auto advance = [&]() {
+        if (++slot == kStages) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      for (int si = 0; si < it.seg_count; ++si) {
+        const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
+        for (int jj = 0; jj < g.n_tiles; ++jj) {
+          const bool a0 = tile_active(g, it, 0, jj);
+          const bool a1 = tile_active(g, it, 1, jj);
+          const uint32_t k_slot = slot, k_phase = phase;
+          advance();
+          const uint32_t v_slot = slot, v_phase = phase;
+          advance();
+          mbar_wait(&bars->kv_full[k_slot], k_phase);
+          tc_fence_after();
+          if (a0) issue_qk(0, k_slot);
+          if (pend1) {  // PV_1 of the previous key tile (its V slot is still resident)
+            mbar_wait(&bars->p_ready[1], p_phase[1]);
+            p_phase[1] ^= 1;
+            tc_fence_after();
+            issue_pv(1, pend1_slot, o_started[1]);
+            o_started[1] = true;
+            umma_commit(&bars->kv_empty[pend1_slot]);
+            pend1 = false;
+          }
+          if (a1) issue_qk(1, k_slot);
+          umma_commit(&bars->kv_empty[k_slot]);
+          mbar_wait(&bars->kv_full[v_slot], v_phase);
+          tc_fence_after();
+          if (a0) {
+            mbar_wait(&bars->p_ready[0], p_phase[0]);
+            p_phase[0] ^= 1;
+            tc_fence_after();
+            issue_pv(0, v_slot, o_started[0]);
+            o_started[0] = true;
+          }
+          if (a1) {
+            pend1 = true;
+            pend1_slot = v_slot;
+          } else {
+            umma_commit(&bars->kv_empty[v_slot]);
+          }
+        }
+      }
+      if (pend1) {
+        mbar_wait(&bars->p_ready[1], p_phase[1]);
+        tc_fence_after();
+        issue_pv(1, pend1_slot, o_started[1]);
+        umma_commit(&bars->kv_empty[pend1_slot]);
+      }
+      umma_commit(&bars->o_done[0]);
+      umma_commit(&bars->o_done[1]);
+    }
+   }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    reg_alloc<216>();
+    const int t = (warp - 4) >> 2;                 // tile handled by this warpgroup
+    const int row_in_tile = ((warp & 3) << 5) | lane;
+    const int n_rows = t == 0 ? n_rows0 : n_rows1;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem + (t == 0 ? kColS0 : kColS1) + lane_addr;
+    const uint32_t t_o = tmem + (t == 0 ? kColO0 : kColO1) + lane_addr;
+    const int chunk_row = it.q_off + t * kTile + row_in_tile;  // row index inside the chunk (diagonal space)
+
+    float m_ref = -CUDART_INF_F;  // reference max (raw score units)
+    float l = 0.f;
+    bool first = true;
+    uint32_t s_phase = 0;
+
+    if (n_rows > 0) {
+      for (int si = 0; si < it.seg_count; ++si) {
+        const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
+        for (int jj = 0; jj < g.n_tiles; ++jj) {
+          if (!tile_active(g, it, t, jj)) continue;
+          mbar_wait(&bars->s_full[t], s_phase);
+          s_phase ^= 1;
+          tc_fence_after();
+
+          uint32_t sr[128];
+          tmem_ld32(t_s + 0, sr + 0);
+          tmem_ld32(t_s + 32, sr + 32);
+          tmem_ld32(t_s + 64, sr + 64);
+          tmem_ld32(t_s + 96, sr + 96);
+          tmem_ld_wait();
+          float s[128];
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] = __uint_as_float(sr[c]);
+
+          if (tile_needs_mask(g, it, t, jj)) {
+            long long lim_ll = static_cast<long long>(chunk_row) + g.diag;
+            if (lim_ll > g.kv_len - 1) lim_ll = g.kv_len - 1;
+            lim_ll -= static_cast<long long>(jj) * kTile;
+            const int lim = lim_ll < -1 ? -1 : (lim_ll > 127 ? 127 : static_cast<int>(lim_ll));
+#pragma unroll
+            for (int c = 0; c < 128; ++c) s[c] = c <= lim ? s[c] : -CUDART_INF_F;
+          }
+
+          float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+          for (int c = 4; c < 128; c += 4) {
+            mx0 = fmaxf(mx0, s[c]);
+            mx1 = fmaxf(mx1, s[c + 1]);
+            mx2 = fmaxf(mx2, s[c + 2]);
+            mx3 = fmaxf(mx3, s[c + 3]);
+          }
+          const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+          // lazy rescale: only move the reference max when it grew by more than the threshold
+          const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? fast_exp2((m_ref - m_new) * p.scale_log2) : 1.0f;
+            if (need) {
+              l *= f;
+              m_ref = m_new;
+            }
+            if (!first) {
+              // S_full for this key tile implies the previous PV of this tile has completed, so O is quiescent.
+#pragma unroll
+              for (int c = 0; c < 128; c += 32) {
+                uint32_t orr[32];
+                tmem_ld32(t_o + c, orr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+                tmem_st32(t_o + c, orr);
+              }
+            }
+          }
+          first = false;
+          const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * p.scale_log2;
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float e0 = fast_exp2(fmaf(s[c + 2 * i], p.scale_log2, -mc));
+              const float e1 = fast_exp2(fmaf(s[c + 2 * i + 1], p.scale_log2, -mc));
+              l0 += e0;
+              l1 += e1;
+              pk[i] = Pack2<T>::pack(e0, e1);
+            }
+            tmem_st16(t_s + (c >> 1), pk);
+          }
+          l += l0 + l1;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->p_ready[t]);
+        }
+      }
+
+      // ---------------------------------------------------------------- epilogue: O / l -> out, lse
+      const int row = it.q_row0 + t * kTile + row_in_tile;
+      const bool row_ok = row_in_tile < n_rows;
+      T* out_row = reinterpret_cast<T*>(p.out) + (static_cast<size_t>(row) * p.hq + head) * kD;
+      if (!first) {
+        mbar_wait(&bars->o_done[t], 0);
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+#pragma unroll
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t orr[32];
+          tmem_ld32(t_o + c, orr);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 v;
+              v.x = Pack2<T>::pack(__uint_as_float(orr[i + 0]) * inv, __uint_as_float(orr[i + 1]) * inv);
+              v.y = Pack2<T>::pack(__uint_as_float(orr[i + 2]) * inv, __uint_as_float(orr[i + 3]) * inv);
+              v.z = Pack2<T>::pack(__uint_as_float(orr[i + 4]) * inv, __uint_as_float(orr[i + 5]) * inv);
+              v.w = Pack2<T>::pack(__uint_as_float(orr[i + 6]) * inv, __uint_as_float(orr[i + 7]) * inv);
+              *reinterpret_cast<uint4*>(out_row + c + i) = v;
+            }
+          }
+        }
+      } else if (row_ok) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(out_row + c) = z;
+      }
+      if (row_ok) {
+        const float lse = l > 0.f ? m_ref * p.scale + __logf(l) : -CUDART_INF_F;
+        const size_t b = row / p.lse_S, sidx = row % p.lse_S;
+        p.lse[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx] = lse;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+}
+
+}  // namespace fwd
+
+const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k, const TensorView& v,
+                            const FwdParams& p, int n_items, cudaStream_t stream) {
+  if (n_items <= 0) return nullptr;
+  CUtensorMap tq, tk, tv;
+  if (const char* e = make_tensor_map(&tq, q, 2, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tk, k, 2, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tv, v, 2, fwd::kTile, fwd::kD)) return e;
+  dim3 grid(n_items, p.hq, 1), block(fwd::kThreads, 1, 1);
+  cudaError_t err;
+  if (dtype == kDtypeBF16) {
+    auto kern = fwd::attn_fwd_kernel<__nv_bfloat16>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    if (err != cudaSuccess) return cudaGetErrorString(err);
+    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, p);
+  } else {
+    auto kern = fwd::attn_fwd_kernel<__half>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    if (err != cudaSuccess) return cudaGetErrorString(err);
+    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, p);
+  }
+  err = cudaGetLastError();
+  return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+}  // namespace rfa

@@ -1,0 +1,160 @@
+// Descriptor probe: single-CTA tcgen05 GEMMs in exactly the operand forms the attention kernels use.
+// Each mode multiplies small matrices whose fp32 product is checked against torch on the host side, so a
+// wrong UMMA shared-memory / instruction descriptor is localised without touching the attention kernels.
+// LBO/SBO/k-step values can be overridden at run time to sweep alternatives in one GPU session.
+#include <stdio.h>
+
+#include "attn_common.h"
+#include "sm100_ptx.cuh"
+
+namespace rfa {
+namespace probe {
+
+struct Smem {
+  uint64_t full;
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+// operand kinds
+//  A: 0 = smem K-major [128 rows][128 k] via TMA      (Q/K/V as A)
+//     1 = TMEM bf16 [128 rows][kdim]                   (P, P^T)
+//     2 = smem K-major [128 rows][64 k] written by threads with the 128B swizzle (dS^T as A)
+//     3 = smem MN-major from a [128 k][128 m] TMA tile (K as A of dQ^T)
+//  B: 0 = smem K-major [n rows][128 k] via TMA         (K as B, Q/dO as B, n = 128 or 64)
+//     1 = smem MN-major from a [kdim rows][128 n] TMA tile (V, Q, dO as B; kdim = 128 or 64)
+//     2 = smem MN-major from thread-written swizzled [128 k][64 n] (dS^T as B)
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+             const __nv_bfloat16* __restrict__ a_raw, const __nv_bfloat16* __restrict__ b_raw,
+             float* __restrict__ out, const ProbeConfig c) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;             // up to 32 KB
+  uint8_t* sb = smem + 32768;     // up to 32 KB
+  Smem* sm = reinterpret_cast<Smem*>(smem + 65536);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&sm->full, 1);
+    mbar_init(&sm->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&sm->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+
+  // ---- operands written by threads
+  if (c.a_kind == 1) {
+    // row `tid`: kdim bf16 values -> kdim/2 packed columns starting at column 256
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a_raw + static_cast<size_t>(tid) * c.kdim);
+    for (int ch = 0; ch < c.kdim / 2; ch += 16) {
+      uint32_t r[16];
+      for (int i = 0; i < 16; ++i) r[i] = src[ch + i];
+      tmem_st16(tmem + 256 + ch + lane_addr, r);
+    }
+    tmem_st_wait();
+  }
+  if (c.a_kind == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(a_raw + static_cast<size_t>(tid) * 64);
+    for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(sa + tid * 128 + ((ch ^ (tid & 7)) << 4)) = src[ch];
+    fence_proxy_async_smem();
+  }
+  if (c.b_kind == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(b_raw + static_cast<size_t>(tid) * 64);
+    for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(sb + tid * 128 + ((ch ^ (tid & 7)) << 4)) = src[ch];
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (tid == 0) {
+    uint32_t bytes = 0;
+    if (c.a_kind == 0 || c.a_kind == 3) bytes += 32768;
+    if (c.b_kind == 0) bytes += c.n * 256;
+    if (c.b_kind == 1) bytes += c.kdim * 256;
+    if (bytes) {
+      mbar_arrive_expect_tx(&sm->full, bytes);
+      if (c.a_kind == 0 || c.a_kind == 3) {
+        tma_load_3d(sa, &tm_a, &sm->full, 0, 0, 0);
+        tma_load_3d(sa + 16384, &tm_a, &sm->full, 64, 0, 0);
+      }
+      if (c.b_kind == 0 || c.b_kind == 1) {
+        const int rows = c.b_kind == 0 ? c.n : c.kdim;
+        tma_load_3d(sb, &tm_b, &sm->full, 0, 0, 0);
+        tma_load_3d(sb + rows * 128, &tm_b, &sm->full, 64, 0, 0);
+      }
+      mbar_wait(&sm->full, 0);
+    }
+    tc_fence_after();
+    const uint32_t a_mn = c.a_kind == 3, b_mn = c.b_kind != 0;
+    const uint32_t idesc = umma_idesc_f16(1, 128, c.n, a_mn, b_mn);
+    const uint32_t sa_u = smem_u32(sa), sb_u = smem_u32(sb);
+    const int b_rows = c.b_kind == 0 ? c.n : c.kdim;  // rows of the B tile as stored
+    for (int k = 0; k < c.kdim / 16; ++k) {
+      uint64_t bd;
+      if (c.b_kind == 0) {
+        bd = umma_smem_desc(sb_u + (k >> 2) * (b_rows * 128) + (k & 3) * 32, c.lbo_b >= 0 ? c.lbo_b : 16,
+                            c.sbo_b >= 0 ? c.sbo_b : 1024, kSwizzle128B);
+      } else if (c.b_kind == 1) {
+        bd = umma_smem_desc(sb_u + k * (c.kstep_b >= 0 ? c.kstep_b : 2048), c.lbo_b >= 0 ? c.lbo_b : b_rows * 128,
+                            c.sbo_b >= 0 ? c.sbo_b : 1024, kSwizzle128B);
+      } else {
+        bd = umma_smem_desc(sb_u + k * (c.kstep_b >= 0 ? c.kstep_b : 2048), c.lbo_b >= 0 ? c.lbo_b : 16,
+                            c.sbo_b >= 0 ? c.sbo_b : 1024, kSwizzle128B);
+      }
+      if (c.a_kind == 1) {
+        umma_ts(tmem, tmem + 256 + k * 8, bd, idesc, k > 0);
+      } else {
+        uint64_t ad;
+        if (c.a_kind == 0) {
+          ad = umma_smem_desc(sa_u + (k >> 2) * 16384 + (k & 3) * 32, c.lbo_a >= 0 ? c.lbo_a : 16,
+                              c.sbo_a >= 0 ? c.sbo_a : 1024, kSwizzle128B);
+        } else if (c.a_kind == 2) {
+          ad = umma_smem_desc(sa_u + k * 32, c.lbo_a >= 0 ? c.lbo_a : 16, c.sbo_a >= 0 ? c.sbo_a : 1024, kSwizzle128B);
+        } else {
+          ad = umma_smem_desc(sa_u + k * (c.kstep_a >= 0 ? c.kstep_a : 2048), c.lbo_a >= 0 ? c.lbo_a : 16384,
+                              c.sbo_a >= 0 ? c.sbo_a : 1024, kSwizzle128B);
+        }
+        umma_ss(tmem, ad, bd, idesc, k > 0);
+      }
+    }
+    umma_commit(&sm->done);
+  }
+  __syncwarp();
+  mbar_wait(&sm->done, 0);
+  tc_fence_after();
+  for (int cc = 0; cc < c.n; cc += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem + cc + lane_addr, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[static_cast<size_t>(tid) * c.n + cc + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace probe
+
+const char* probe_launch(const TensorView& a, const TensorView& b, const void* a_raw, const void* b_raw, float* out,
+                         const ProbeConfig& c, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  TensorView dummy = a.ptr ? a : b;
+  if (const char* e = make_tensor_map(&ta, a.ptr ? a : dummy, 2, 128, 128)) return e;
+  const int b_rows = c.b_kind == 0 ? c.n : c.kdim;
+  if (const char* e = make_tensor_map(&tb, b.ptr ? b : dummy, 2, b_rows, 128)) return e;
+  const int smem = 65536 + 1024 + 1024;
+  cudaError_t err = cudaFuncSetAttribute(probe::probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return cudaGetErrorString(err);
+  probe::probe_kernel<<<1, 128, smem, stream>>>(ta, tb, static_cast<const __nv_bfloat16*>(a_raw),
+                                                static_cast<const __nv_bfloat16*>(b_raw), out, c);
+  err = cudaGetLastError();
+  return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+}  // namespace rfa

@@ -1,0 +1,185 @@
+"""Python side of the sm_100a attention kernels: plan -> device work tables -> launches.
+
+The kernels (``csrc/attn_fwd_sm100.cu`` / ``attn_bwd_sm100.cu``) consume a :class:`CPPlan` as two small
+int32 tables.  Tables are cached on the plan object (plans themselves are lru-cached per shape), so the
+steady state of a training loop performs no host work beyond the launches.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import cuda_ext
+from .plan import CPPlan, Segment
+
+DIAG_FULL = 1 << 29
+Q_ITEM_ROWS = 256  # rows per forward CTA (two 128-row MMA tiles)
+K_TILE_ROWS = 128  # keys per backward CTA
+
+
+def supported(q: torch.Tensor, k: torch.Tensor) -> bool:
+    return q.shape[-1] == 128 and q.dtype in (torch.bfloat16, torch.float16) and k.dtype == q.dtype
+
+
+def _diag(d: Optional[int]) -> int:
+    return DIAG_FULL if d is None else int(d)
+
+
+# ----------------------------------------------------------------------------------------------
+# forward tables
+# ----------------------------------------------------------------------------------------------
+
+def fwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int],
+                    flag_of_src: Optional[Dict[int, int]] = None) -> Tuple[List[List[int]], List[List[int]], bool]:
+    """(items, segments, all_chunks_covered).  ``row_offset[src]`` is where source ``src``'s shard
+    starts inside the K/V tensor handed to the launch; ``flag_of_src`` (fused mode) maps a source to
+    the ready flag the loader must wait on."""
+    by_chunk: Dict[int, List[Segment]] = {}
+    for s in segs:
+        by_chunk.setdefault(s.chunk, []).append(s)
+    items, seg_rows = [], []
+    for ci, ch in enumerate(plan.q_chunks):
+        cs = by_chunk.get(ci)
+        if not cs or ch.rows == 0:
+            continue
+        begin = len(seg_rows)
+        for s in cs:
+            flag = -1 if flag_of_src is None else flag_of_src.get(s.src, -1)
+            seg_rows.append([row_offset[s.src] + s.kv_row0, s.kv_len, _diag(s.diag), flag])
+        for off in range(0, ch.rows, Q_ITEM_ROWS):
+            rows = min(Q_ITEM_ROWS, ch.rows - off)
+            work = 0
+            for s in cs:
+                d = _diag(s.diag)
+                work += max(0, min(s.kv_len, off + rows + d))
+            items.append((work, [ch.row0 + off, rows, off, begin, len(cs), 0, 0, 0]))
+    items.sort(key=lambda t: -t[0])  # heaviest first
+    covered = all((ci in by_chunk) or ch.rows == 0 for ci, ch in enumerate(plan.q_chunks))
+    return [it for _, it in items], seg_rows, covered
+
+
+def bwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int],
+                    flag_of_src: Optional[Dict[int, int]] = None):
+    """Backward tables: key tiles that exclusively own their dK/dV rows + the query chunks that see them."""
+    by_src: Dict[int, List[Segment]] = {}
+    for s in segs:
+        by_src.setdefault(s.src, []).append(s)
+    items, qsegs = [], []
+    for src, ss in by_src.items():
+        cuts = sorted({s.kv_row0 for s in ss} | {s.kv_row0 + s.kv_len for s in ss})
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            cover = [s for s in ss if s.kv_row0 <= lo and s.kv_row0 + s.kv_len >= hi]
+            if not cover:
+                continue
+            for t0 in range(lo, hi, K_TILE_ROWS):
+                rows = min(K_TILE_ROWS, hi - t0)
+                begin = len(qsegs)
+                work = 0
+                for s in cover:
+                    ch = plan.q_chunks[s.chunk]
+                    d = DIAG_FULL if s.diag is None else s.diag - (t0 - s.kv_row0)
+                    if ch.rows - 1 + d < 0:
+                        continue  # no query of this chunk reaches the tile
+                    qsegs.append([ch.row0, ch.rows, d, 0])
+                    work += ch.rows - max(0, -d)
+                if len(qsegs) == begin:
+                    continue
+                flag = -1 if flag_of_src is None else flag_of_src.get(src, -1)
+                items.append((work, [row_offset[src] + t0, rows, begin, len(qsegs) - begin, flag, 0, 0, 0]))
+    items.sort(key=lambda t: -t[0])
+    return [it for _, it in items], qsegs
+
+
+def _to_dev(rows: List[List[int]], width: int, device) -> torch.Tensor:
+    if not rows:
+        return torch.zeros((0, width), dtype=torch.int32, device=device)
+    return torch.tensor(rows, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def _cache(plan: CPPlan) -> dict:
+    c = getattr(plan, "_cuda_tables", None)
+    if c is None:
+        c = {}
+        plan._cuda_tables = c
+    return c
+
+
+def fwd_tables(plan, segs, row_offset, device, key, flag_of_src=None):
+    c = _cache(plan)
+    k = ("fwd", key, device.index)
+    if k not in c:
+        items, seg_rows, covered = fwd_tables_host(plan, segs, row_offset, flag_of_src)
+        c[k] = (_to_dev(items, 8, device), _to_dev(seg_rows, 4, device), covered)
+    return c[k]
+
+
+def bwd_tables(plan, segs, row_offset, device, key, flag_of_src=None):
+    c = _cache(plan)
+    k = ("bwd", key, device.index)
+    if k not in c:
+        items, qsegs = bwd_tables_host(plan, segs, row_offset, flag_of_src)
+        c[k] = (_to_dev(items, 8, device), _to_dev(qsegs, 4, device))
+    return c[k]
+
+
+# ----------------------------------------------------------------------------------------------
+# launches
+# ----------------------------------------------------------------------------------------------
+
+def _rows3(t: torch.Tensor) -> torch.Tensor:
+    """The kernels take (rows, heads, 128) views with a unit inner stride and 16-byte aligned strides."""
+    if t.stride(-1) != 1 or (t.stride(0) * t.element_size()) % 16 or (t.stride(1) * t.element_size()) % 16 \
+            or t.data_ptr() % 16:
+        return t.contiguous()
+    return t
+
+
+def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None, ready_flags=None, ready_epoch=0):
+    """Run the forward kernel over prepared tables.  Returns (out (Tq,Hq,128) in q.dtype, lse (Hq,Tq) fp32)."""
+    C = cuda_ext.load()
+    tq, hq, d = q.shape
+    if out is None:
+        out = (torch.empty if covered else torch.zeros)((tq, hq, d), dtype=q.dtype, device=q.device)
+    if lse is None:
+        lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
+        if not covered:
+            lse.fill_(float("-inf"))
+    if items.shape[0]:
+        C.attn_fwd(_rows3(q), _rows3(k), _rows3(v), items, segs, out, lse, tq, float(scale), ready_flags,
+                   int(ready_epoch))
+        cuda_ext.note_launch()
+    return out, lse
+
+
+def segments_forward(plan: CPPlan, segs: Sequence[Segment], q, k_src, v_src, scale):
+    """Partial attention of the local queries against ONE source shard (torch.distributed fallback path)."""
+    src = segs[0].src
+    items, seg_t, covered = fwd_tables(plan, segs, {src: 0}, q.device, ("step", src))
+    return forward_launch(q, k_src, v_src, items, seg_t, covered, scale)
+
+
+def compute_delta(out, dout, hq_rows=None) -> torch.Tensor:
+    C = cuda_ext.load()
+    tq, hq, _ = out.shape
+    delta = torch.empty((hq, tq), dtype=torch.float32, device=out.device)
+    C.attn_bwd_delta(_rows3(out), _rows3(dout), delta, tq)
+    cuda_ext.note_launch()
+    return delta
+
+
+def backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq_accum, dk, dv, ready_flags=None,
+                    ready_epoch=0):
+    C = cuda_ext.load()
+    if items.shape[0]:
+        C.attn_bwd(_rows3(q), _rows3(dout), _rows3(k), _rows3(v), dq_accum, items, qsegs, lse, delta, dk, dv,
+                   q.shape[0], float(scale), ready_flags, int(ready_epoch))
+        cuda_ext.note_launch()
+
+
+def segments_backward(plan: CPPlan, segs: Sequence[Segment], dout, q, k_src, v_src, lse, delta, scale, dq, dk, dv,
+                      deterministic=False):
+    """Gradient contribution of ONE source shard: dq (fp32) accumulates, dk/dv (fp32, zeroed) are filled."""
+    src = segs[0].src
+    items, qsegs = bwd_tables(plan, segs, {src: 0}, q.device, ("step", src))
+    backward_launch(q, dout, k_src, v_src, lse.contiguous(), delta.contiguous(), items, qsegs, scale, dq, dk, dv)

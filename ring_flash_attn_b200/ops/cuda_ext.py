@@ -38,3 +38,24 @@ def available_for(t: torch.Tensor) -> bool:
         return False
     load()
     return True
+
+
+class _LaunchCounter:
+    """Counts launches of this library's own kernels (bench.py reports it as ``gpu_launches``)."""
+
+    def __init__(self):
+        self.value = 0
+
+    def reset(self):
+        self.value = 0
+
+
+_COUNTER = _LaunchCounter()
+
+
+def launch_counter() -> _LaunchCounter:
+    return _COUNTER
+
+
+def note_launch(n: int = 1) -> None:
+    _COUNTER.value += n

@@ -30,19 +30,24 @@ from .comm import AllGatherComm, RingComm
 # per-source block execution (one ring step / one gathered slab)
 # ----------------------------------------------------------------------------------------------
 
-def _use_cuda_kernels(t: torch.Tensor) -> bool:
-    if not t.is_cuda:
-        return False
-    from ..ops import cuda_ext
+def _use_cuda_kernels(q: torch.Tensor, k: Optional[torch.Tensor] = None) -> bool:
+    """True when the sm_100a kernels handle this call (Blackwell GPU, bf16/fp16, head_dim 128).
 
-    return cuda_ext.available_for(t)
+    Other CUDA inputs (e.g. head_dim 64) run the dense torch blocks on the GPU - slow but correct."""
+    if not q.is_cuda:
+        return False
+    from ..ops import attn_cuda, cuda_ext
+
+    if not cuda_ext.available_for(q):
+        return False
+    return attn_cuda.supported(q, q if k is None else k)
 
 
 def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out, lse):
     """Fold the contribution of one source shard into the running (out, lse)."""
     if not segs:
         return out, lse
-    if _use_cuda_kernels(q):
+    if _use_cuda_kernels(q, k_src):
         from ..ops import attn_cuda
 
         p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
@@ -66,7 +71,7 @@ def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse,
     dv = torch.zeros(v_src.shape, dtype=torch.float32, device=q.device)
     if not segs:
         return dk, dv
-    if _use_cuda_kernels(q):
+    if _use_cuda_kernels(q, k_src):
         from ..ops import attn_cuda
 
         attn_cuda.segments_backward(plan, segs, dout, q, k_src, v_src, lse, delta, scale, dq, dk, dv,
@@ -231,8 +236,8 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 # entry points used by the autograd bridge
 # ----------------------------------------------------------------------------------------------
 
-def _fused_ok(q: torch.Tensor, group) -> bool:
-    if not _use_cuda_kernels(q):
+def _fused_ok(q: torch.Tensor, k: torch.Tensor, group) -> bool:
+    if not _use_cuda_kernels(q, k):
         return False
     from . import fused
 
@@ -240,7 +245,7 @@ def _fused_ok(q: torch.Tensor, group) -> bool:
 
 
 def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_stride: int = 1):
-    if _fused_ok(q, group):
+    if _fused_ok(q, k, group):
         from . import fused
 
         return fused.forward(plan, q, k, v, scale, group)
@@ -251,7 +256,7 @@ def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_st
 
 def cp_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, transport="ring",
                 heads_k_stride: int = 1, deterministic: bool = False):
-    if _fused_ok(q, group):
+    if _fused_ok(q, k, group):
         from . import fused
 
         return fused.backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)

@@ -1,0 +1,62 @@
+"""Fused sm_100a execution of a context-parallel plan.
+
+``world == 1``: one forward launch and one backward launch over the whole plan.
+``world > 1`` : the same kernels, with every remote K/V shard arriving through peer-mapped staging
+buffers that the *attention kernel's own communication CTAs* fill over NVLink while the math on the
+local shard runs (``parallel/symm.py`` + ``csrc/comm_sm100.cu``).  No NCCL call is on this path.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from ..ops import attn_cuda
+from ..ops.plan import CPPlan
+from .comm import group_info
+
+
+def available(q: torch.Tensor, group) -> bool:
+    _rank, world = group_info(group)
+    if world == 1:
+        return True
+    if os.environ.get("RFA_B200_DISABLE_P2P", "0") == "1":
+        return False
+    from . import symm
+
+    return symm.peer_context(group, q.device) is not None
+
+
+# ----------------------------------------------------------------------------------------------
+# single GPU
+# ----------------------------------------------------------------------------------------------
+
+def _forward_local(plan: CPPlan, q, k, v, scale):
+    items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
+    return attn_cuda.forward_launch(q, k, v, items, segs, covered, scale)
+
+
+def _backward_local(plan: CPPlan, dout, q, k, v, out, lse, scale):
+    items, qsegs = attn_cuda.bwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
+    delta = attn_cuda.compute_delta(out, dout)
+    dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    dk = torch.zeros(k.shape, dtype=torch.float32, device=q.device)
+    dv = torch.zeros(v.shape, dtype=torch.float32, device=q.device)
+    attn_cuda.backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq, dk, dv)
+    return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
+
+
+def forward(plan: CPPlan, q, k, v, scale, group):
+    if plan.world == 1:
+        return _forward_local(plan, q, k, v, scale)
+    from . import symm
+
+    return symm.fused_forward(plan, q, k, v, scale, group)
+
+
+def backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, deterministic=False):
+    if plan.world == 1:
+        return _backward_local(plan, dout, q, k, v, out, lse, scale)
+    from . import symm
+
+    return symm.fused_backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)

@@ -1,0 +1,164 @@
+"""sm_100a kernels against the plain fp32 PyTorch oracle (run with -m gpu on a B200)."""
+import math
+
+import pytest
+import torch
+
+import ring_flash_attn_b200 as rfa
+from ring_flash_attn_b200.ops import plan as P
+from ring_flash_attn_b200.ops.dense import attention_oracle, block_bwd, block_fwd, varlen_attention_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _ext():
+    from ring_flash_attn_b200.ops import cuda_ext
+
+    return cuda_ext.load()
+
+
+def test_extension_is_loaded_and_native():
+    C = _ext()
+    assert hasattr(C, "attn_fwd") and hasattr(C, "attn_bwd")
+    assert torch.cuda.get_device_capability()[0] == 10, "these tests expect a Blackwell (sm_100) GPU"
+
+
+def test_descriptor_probe_all_forms():
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "probe_descriptors", os.path.join(os.path.dirname(__file__), "..", "benchmark", "probe_descriptors.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    C = _ext()
+    for name in mod.MODES:
+        err, mag = mod.run(C, name)
+        assert err < 2e-2 * max(mag, 1.0), f"{name}: max err {err}"
+
+
+def _rand(shape, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, device="cuda", generator=g, dtype=torch.float32).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sq,sk,hq,hkv,diag", [
+    (128, 128, 1, 1, None), (128, 128, 1, 1, 0), (256, 256, 2, 1, 0), (384, 512, 4, 2, 128),
+    (200, 333, 2, 2, 40), (77, 50, 1, 1, None), (300, 300, 2, 2, -1), (512, 1024, 2, 1, None),
+])
+def test_fwd_block_kernel(dtype, sq, sk, hq, hkv, diag):
+    """One chunk x one segment through the tcgen05 forward kernel vs dense fp32."""
+    from ring_flash_attn_b200.ops import attn_cuda
+
+    q, k, v = _rand((sq, hq, 128), dtype, 1), _rand((sk, hkv, 128), dtype, 2), _rand((sk, hkv, 128), dtype, 3)
+    scale = 1 / math.sqrt(128)
+    plan = P.CPPlan(1, 0, sq, sk, [P.QChunk(0, sq)], [P.Segment(0, 0, 0, sk, diag)])
+    out, lse = attn_cuda.segments_forward(plan, plan.segments, q, k, v, scale)
+    ref_out, ref_lse = block_fwd(q, k, v, scale, diag)
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("sq,sk,hq,hkv,diag", [
+    (128, 128, 1, 1, None), (128, 128, 1, 1, 0), (256, 256, 2, 1, 0), (384, 512, 4, 2, 128),
+    (200, 333, 2, 2, 40), (77, 50, 1, 1, None), (300, 300, 2, 2, -1),
+])
+def test_bwd_block_kernel(sq, sk, hq, hkv, diag):
+    from ring_flash_attn_b200.ops import attn_cuda
+
+    dtype = torch.bfloat16
+    q, k, v = _rand((sq, hq, 128), dtype, 1), _rand((sk, hkv, 128), dtype, 2), _rand((sk, hkv, 128), dtype, 3)
+    dout = _rand((sq, hq, 128), dtype, 4)
+    scale = 1 / math.sqrt(128)
+    ref_out, ref_lse = block_fwd(q, k, v, scale, diag)
+    delta = (ref_out * dout.float()).sum(-1).transpose(0, 1).contiguous()
+    ref_dq, ref_dk, ref_dv = block_bwd(dout, q, k, v, ref_lse, delta, scale, diag)
+    plan = P.CPPlan(1, 0, sq, sk, [P.QChunk(0, sq)], [P.Segment(0, 0, 0, sk, diag)])
+    dq = torch.zeros(sq, hq, 128, device="cuda")
+    dk = torch.zeros(sk, hkv, 128, device="cuda")
+    dv = torch.zeros(sk, hkv, 128, device="cuda")
+    attn_cuda.segments_backward(plan, plan.segments, dout, q, k, v, ref_lse, delta, scale, dq, dk, dv)
+    for got, want, name in ((dq, ref_dq, "dq"), (dk, ref_dk, "dk"), (dv, ref_dv, "dv")):
+        err = (got - want).abs().max().item()
+        assert err < 3e-2 * max(1.0, want.abs().max().item()), f"{name}: {err}"
+
+
+def test_delta_kernel():
+    from ring_flash_attn_b200.ops import attn_cuda
+
+    o, do = _rand((333, 3, 128), torch.bfloat16, 5), _rand((333, 3, 128), torch.bfloat16, 6)
+    got = attn_cuda.compute_delta(o, do)
+    want = (o.float() * do.float()).sum(-1).transpose(0, 1)
+    torch.testing.assert_close(got, want, atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("fn_name", ["ring_flash_attn_qkvpacked_func", "zigzag_ring_flash_attn_qkvpacked_func",
+                                     "stripe_flash_attn_qkvpacked_func"])
+def test_world1_api_matches_oracle(fn_name):
+    """world_size 1 through the public API: every scheme is causal flash attention (fwd + bwd)."""
+    torch.manual_seed(0)
+    qkv = (torch.randn(2, 640, 3, 4, 128, device="cuda") * 0.7).to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(2, 640, 4, 128, device="cuda").to(torch.bfloat16)
+    ref = qkv.detach().float().requires_grad_(True)
+    ref_out, ref_lse = attention_oracle(ref[:, :, 0], ref[:, :, 1], ref[:, :, 2], True)
+    ref_out.backward(dout.float())
+    out, lse, _ = getattr(rfa, fn_name)(qkv, causal=True, return_attn_probs=True)
+    out.backward(dout)
+    torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    assert (qkv.grad.float() - ref.grad).abs().max().item() < 5e-2 * ref.grad.abs().max().item() + 2e-2
+
+
+def test_world1_gqa_kvpacked_noncausal():
+    torch.manual_seed(0)
+    q = torch.randn(1, 500, 8, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    kv = torch.randn(1, 500, 2, 2, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(1, 500, 8, 128, device="cuda").to(torch.bfloat16)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    ref_out, _ = attention_oracle(rq, rkv[:, :, 0], rkv[:, :, 1], False)
+    ref_out.backward(dout.float())
+    out = rfa.ring_flash_attn_kvpacked_func(q, kv, causal=False)
+    out.backward(dout)
+    torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+    assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
+    assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
+
+
+def test_world1_varlen_and_llama3():
+    torch.manual_seed(0)
+    cu = torch.tensor([0, 120, 1248, 2000], dtype=torch.int32, device="cuda")
+    total = 2000
+    qkv = torch.randn(total, 3, 4, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(total, 4, 128, device="cuda").to(torch.bfloat16)
+    ref = qkv.detach().float().requires_grad_(True)
+    ref_out, ref_lse = varlen_attention_oracle(ref[:, 0], ref[:, 1], ref[:, 2], cu.cpu(), True)
+    ref_out.backward(dout.float())
+    for which in ("ring", "zigzag", "llama3"):
+        qkv.grad = None
+        if which == "llama3":
+            cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu, True, 0, 1)
+            out, lse, _ = rfa.llama3_flash_attn_varlen_qkvpacked_func(
+                qkv, cq, ck, mq, mk, heads_k_stride=1, local_k_slice=ks, causal=True, return_attn_probs=True)
+        else:
+            fn = rfa.ring_flash_attn_varlen_qkvpacked_func if which == "ring" \
+                else rfa.zigzag_ring_flash_attn_varlen_qkvpacked_func
+            out, lse, _ = fn(qkv, cu, 1128, causal=True, return_attn_probs=True)
+        out.backward(dout)
+        torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+        torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+        assert (qkv.grad.float() - ref.grad).abs().max().item() < 5e-2 * ref.grad.abs().max().item() + 2e-2
+
+
+def test_lse_layout_kernels_match_torch():
+    from ring_flash_attn_b200.ops import lse_layout
+
+    cu = torch.tensor([0, 5, 133, 400], dtype=torch.int32, device="cuda")
+    lse = torch.randn(3, 4, 267, device="cuda")
+    flat = lse_layout.flatten_varlen_lse(lse, cu)
+    assert torch.equal(flat, lse_layout._flatten_torch(lse, cu))
+    packed = torch.randn(400, 4, 1, device="cuda")
+    un = lse_layout.unflatten_varlen_lse(packed, cu, 267)
+    ref = lse_layout._unflatten_torch(packed, cu, 267)
+    for b, (a, e) in enumerate(zip([0, 5, 133], [5, 133, 400])):
+        assert torch.equal(un[b, :, : e - a], ref[b, :, : e - a])
