@@ -21,6 +21,7 @@
 #include <stdio.h>
 
 #include "attn_common.h"
+#include "comm_device.cuh"
 #include "sm100_ptx.cuh"
 
 namespace rfa {
@@ -81,7 +82,14 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                const __grid_constant__ CUtensorMap tm_dq, const BwdParams p) {
+                const __grid_constant__ CUtensorMap tm_ks, const __grid_constant__ CUtensorMap tm_vs,
+                const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ BwdParams p) {
+  // communication CTAs first (see comm_device.cuh): they re-publish this rank's K/V rows to the peers
+  if (static_cast<int>(blockIdx.x) < p.push.n_ctas) {
+    push_role(p.push);
+    return;
+  }
+  const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_k = smem;
@@ -94,9 +102,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kv_head = blockIdx.y;
+  const int kv_head = cta / p.n_items;
   const int group = p.hq / p.hkv;
-  const BwdItem it = p.items[blockIdx.x];
+  const BwdItem it = p.items[cta % p.n_items];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -104,6 +112,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_dq);
+    tma_prefetch_desc(&tm_ks);
+    tma_prefetch_desc(&tm_vs);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(&bars->kv_full, 1);
@@ -137,19 +147,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int total_tiles = tiles_per_head * group;
 
   if (warp < 4) {
-    reg_dealloc<80>();
+    reg_dealloc<72>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
-        if (it.flag >= 0 && p.ready_flags != nullptr) {
-          wait_flag_ge(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready");
+        const bool staged = it.flag >= 0 && p.ready_flags != nullptr;
+        if (staged) {
+          wait_epoch(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready");
           fence_proxy_async_all();
         }
+        const CUtensorMap* mk = staged ? &tm_ks : &tm_k;
+        const CUtensorMap* mv = staged ? &tm_vs : &tm_v;
         mbar_arrive_expect_tx(&bars->kv_full, 2 * kKVBytes);
-        tma_load_3d(smem_k, &tm_k, &bars->kv_full, 0, kv_head, it.kv_row0);
-        tma_load_3d(smem_k + kKVHalf, &tm_k, &bars->kv_full, 64, kv_head, it.kv_row0);
-        tma_load_3d(smem_v, &tm_v, &bars->kv_full, 0, kv_head, it.kv_row0);
-        tma_load_3d(smem_v + kKVHalf, &tm_v, &bars->kv_full, 64, kv_head, it.kv_row0);
+        tma_load_3d(smem_k, mk, &bars->kv_full, 0, kv_head, it.kv_row0);
+        tma_load_3d(smem_k + kKVHalf, mk, &bars->kv_full, 64, kv_head, it.kv_row0);
+        tma_load_3d(smem_v, mv, &bars->kv_full, 0, kv_head, it.kv_row0);
+        tma_load_3d(smem_v + kKVHalf, mv, &bars->kv_full, 64, kv_head, it.kv_row0);
         uint32_t slot = 0, phase = 0;
         for (int gq = 0; gq < group; ++gq) {
           const int head = kv_head * group + gq;
@@ -390,14 +403,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     // ---------------------------------------------------------------- epilogue: dK / dV tile -> global (fp32)
-    const int row = it.kv_row0 + key;
+    const bool remote = p.dkv.world > 0;
+    const int row = (remote ? it.out_row0 : it.kv_row0) + key;
+    if (remote && wg_tid == 0) {
+      // the owner must have drained what we stored into its inbox during the previous backward call
+      wait_epoch(p.dkv.my_pad + kPadInboxFree + it.owner, p.dkv.wait_epoch, "inbox reuse");
+    }
+    if (remote) named_bar_sync(1, 128);
     if (total_tiles > 0) {
       mbar_wait(&bars->dkv_done, 0);
       tc_fence_after();
     }
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      float* dst = (which == 0 ? p.dk : p.dv) + (static_cast<size_t>(row) * p.hkv + kv_head) * kD;
+      float* base = remote ? (which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner])
+                           : (which == 0 ? p.dk : p.dv);
+      float* dst = base + (static_cast<size_t>(row) * p.hkv + kv_head) * kD;
       const uint32_t col = tmem + (which == 0 ? kColDK : kColDV) + lane_addr;
 #pragma unroll
       for (int c = 0; c < 128; c += 32) {
@@ -413,6 +434,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
             *reinterpret_cast<uint4*>(dst + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        }
+      }
+    }
+    if (remote) {
+      // publish: the last tile destined for an owner raises that owner's "gradients landed" flag
+      __threadfence_system();
+      named_bar_sync(1, 128);
+      if (wg_tid == 0) {
+        const uint32_t old = atomicAdd(p.dkv.sent_count + it.owner, 1u);
+        if (old + 1u == p.dkv.sent_target[it.owner]) {
+          __threadfence_system();
+          st_release_sys(p.dkv.peer_pads[it.owner] + kPadDkvReady + p.dkv.my_rank, p.dkv.epoch);
         }
       }
     }
@@ -457,6 +490,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+  if (threadIdx.x == 0 && p.sig.world > 0) consumer_done(p.sig);
 }
 
 // delta[h, t] = sum_d out[t,h,d] * dout[t,h,d]; one warp per (row, head).
@@ -506,27 +540,30 @@ const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const Tensor
 }
 
 const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& dout, const TensorView& k,
-                            const TensorView& v, const TensorView& dq_accum, const BwdParams& p, int n_items,
-                            cudaStream_t stream) {
-  if (n_items <= 0) return nullptr;
-  CUtensorMap tq, tdo, tk, tv, tdq;
+                            const TensorView& v, const TensorView& k_stage, const TensorView& v_stage,
+                            const TensorView& dq_accum, const BwdParams& p, cudaStream_t stream) {
+  const int n_blocks = p.push.n_ctas + p.n_items * p.hkv;
+  if (n_blocks <= 0) return nullptr;
+  CUtensorMap tq, tdo, tk, tv, tks, tvs, tdq;
   if (const char* e = make_tensor_map(&tq, q, 2, bwd::kTileQ, bwd::kD)) return e;
   if (const char* e = make_tensor_map(&tdo, dout, 2, bwd::kTileQ, bwd::kD)) return e;
   if (const char* e = make_tensor_map(&tk, k, 2, bwd::kTileK, bwd::kD)) return e;
   if (const char* e = make_tensor_map(&tv, v, 2, bwd::kTileK, bwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tks, k_stage, 2, bwd::kTileK, bwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tvs, v_stage, 2, bwd::kTileK, bwd::kD)) return e;
   if (const char* e = make_plain_tensor_map(&tdq, dq_accum, 4, bwd::kTileQ, bwd::kD)) return e;
-  dim3 grid(n_items, p.hkv, 1), block(bwd::kThreads, 1, 1);
+  dim3 grid(n_blocks, 1, 1), block(bwd::kThreads, 1, 1);
   cudaError_t err;
   if (dtype == kDtypeBF16) {
     auto kern = bwd::attn_bwd_kernel<__nv_bfloat16>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
     if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tdq, p);
+    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   } else {
     auto kern = bwd::attn_bwd_kernel<__half>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
     if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tdq, p);
+    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   }
   err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

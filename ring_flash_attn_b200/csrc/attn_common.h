@@ -35,6 +35,89 @@ struct TensorView {
   int64_t head_stride;
 };
 
+// ---- cross-GPU signalling (fused multi-GPU mode) ------------------------------------------------------
+// Every rank owns a "signal pad" of uint32 epochs that its peers write over NVLink.
+constexpr int kMaxRanks = 16;
+constexpr int kPadKvReady = 0;      // [src]   src's K/V rows for me have landed in my staging buffer
+constexpr int kPadConsumed = 64;    // [dst]   dst has finished reading what I pushed (staging reusable)
+constexpr int kPadDkvReady = 128;   // [src]   src's dK/dV partials for my shard have landed in my inbox
+constexpr int kPadInboxFree = 192;  // [owner] owner has reduced its inbox (I may overwrite my slot there)
+constexpr int kPadWords = 1024;
+
+// One contiguous run of K (or V) rows to copy from local memory into a peer's staging buffer.
+// Offsets (not pointers) so that the table depends only on the plan and can be cached on the device.
+struct alignas(16) PushTask {
+  long long src_off;  // bytes from the local K (which == 0) or V (which == 1) base to the first row
+  long long dst_off;  // bytes from the destination's staging base to the first staged row
+  int rows;
+  int dst;    // destination rank
+  int which;  // 0 = K, 1 = V
+  int pad;
+};
+
+struct PushParams {
+  const PushTask* tasks;
+  int n_tasks;
+  int n_ctas;     // blocks [0, n_ctas) of the grid are push CTAs
+  int row_bytes;  // bytes per staged row (kv heads * 128 * 2)
+  int my_rank;
+  uint32_t epoch;
+  const char* src_base[2];      // local K / V
+  long long src_row_bytes[2];   // local row pitch of K / V
+  char* stage_ptrs[kMaxRanks];  // peer-mapped staging base of every rank
+  uint32_t* my_pad;
+  uint32_t* peer_pads[kMaxRanks];
+  uint32_t* sent_count;                // device counters, one per destination (cumulative)
+  uint32_t sent_target[kMaxRanks];     // counter value that means "everything for this destination is out"
+};
+
+struct SignalParams {
+  uint32_t* peer_pads[kMaxRanks];
+  uint32_t* done_count;  // device counter (cumulative over calls)
+  uint32_t done_target;
+  uint32_t epoch;
+  int world;    // 0 = signalling disabled
+  int my_rank;
+};
+
+// Backward: where dK/dV tiles go.  owner slot o = (fp32 inbox of rank o, slot reserved for this rank).
+struct DkvParams {
+  float* dk_ptrs[kMaxRanks];
+  float* dv_ptrs[kMaxRanks];
+  uint32_t* peer_pads[kMaxRanks];
+  uint32_t* my_pad;
+  uint32_t* sent_count;               // device counters per owner (cumulative)
+  uint32_t sent_target[kMaxRanks];
+  uint32_t epoch;
+  uint32_t wait_epoch;  // epoch of the previous backward call: owners must have reduced it before we overwrite
+  int world;  // 0 = disabled: write to BwdParams::dk / dv
+  int my_rank;
+};
+
+// Owner-side reduction of the fp32 inbox into dK / dV (csrc/comm_sm100.cu).
+struct alignas(16) ReduceTask {
+  int row0, rows;
+  unsigned src_mask;  // ranks whose slot holds a partial for these rows
+  int pad;
+};
+struct ReduceParams {
+  const ReduceTask* tasks;
+  int n_tasks;
+  const float* inbox;     // [world][2][rows_cap * hkv * 128]
+  long long slot_stride;  // floats between slots
+  long long kv_stride;    // floats between the dK and dV halves of a slot
+  void* dk;               // (rows, hkv, 128) contiguous, output dtype
+  void* dv;
+  int row_elems;          // hkv * 128
+  const uint32_t* my_pad;
+  uint32_t* peer_pads[kMaxRanks];
+  uint32_t* ticket;       // device counter (cumulative)
+  uint32_t ticket_target;
+  uint32_t epoch;
+  int world, my_rank;
+};
+const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream);
+
 struct FwdParams {
   const WorkItem* items;
   const KVSegment* segs;
@@ -44,8 +127,11 @@ struct FwdParams {
   int hq, hkv;
   float scale;       // softmax scale
   float scale_log2;  // scale * log2(e)
-  const uint32_t* ready_flags;  // fused mode only
+  const uint32_t* ready_flags;  // fused mode only: this rank's signal pad (kPadKvReady + src)
   uint32_t ready_epoch;
+  int n_items;       // compute CTAs = n_items * hq, laid out after the push CTAs
+  PushParams push;   // n_ctas == 0 when there is nothing to push
+  SignalParams sig;
 };
 
 // Backward work item: one tile of <= 128 keys (exclusive owner of those dK/dV rows in this launch).
@@ -55,7 +141,9 @@ struct alignas(16) BwdItem {
   int seg_begin;  // first entry in the query-segment table
   int seg_count;
   int flag;  // fused mode: index of the "keys have landed" flag, -1 = local data
-  int pad0, pad1, pad2;
+  int owner;     // fused mode: rank that owns these keys (selects the dK/dV destination)
+  int out_row0;  // row of the tile inside the owner's shard (== kv_row0 when not fused)
+  int pad2;
 };
 // A query chunk that can see the key tile.  tile key j visible to chunk row i  iff  j <= i + diag.
 struct alignas(16) BwdQSegment {
@@ -77,6 +165,10 @@ struct BwdParams {
   float scale, scale_log2;
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
+  int n_items;
+  PushParams push;
+  SignalParams sig;
+  DkvParams dkv;
 };
 
 // Descriptor probe (csrc/probe_sm100.cu): operand forms + optional run-time overrides (-1 = kernel default).
@@ -92,14 +184,16 @@ struct ProbeConfig {
 enum : int { kDtypeBF16 = 0, kDtypeFP16 = 1 };
 
 // ---- launchers (implemented in the .cu files; plain C++ so bindings.cpp needs no CUDA headers beyond runtime)
+// k_stage / v_stage: the peer-filled staging tensors read by segments with flag >= 0 (pass k / v when unused).
 const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k, const TensorView& v,
-                            const FwdParams& p, int n_items, cudaStream_t stream);
+                            const TensorView& k_stage, const TensorView& v_stage, const FwdParams& p,
+                            cudaStream_t stream);
 
 const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const TensorView& dout, float* delta, int lse_S,
                                   cudaStream_t stream);
 const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& dout, const TensorView& k,
-                            const TensorView& v, const TensorView& dq_accum, const BwdParams& p, int n_items,
-                            cudaStream_t stream);
+                            const TensorView& v, const TensorView& k_stage, const TensorView& v_stage,
+                            const TensorView& dq_accum, const BwdParams& p, cudaStream_t stream);
 const char* probe_launch(const TensorView& a, const TensorView& b, const void* a_raw, const void* b_raw, float* out,
                          const ProbeConfig& c, cudaStream_t stream);
 const char* lse_flatten_launch(const float* in, float* out, const int* cu, int batch, int heads, int max_seqlen,

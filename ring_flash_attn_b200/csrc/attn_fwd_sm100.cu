@@ -20,6 +20,7 @@
 #include <stdio.h>
 
 #include "attn_common.h"
+#include "comm_device.cuh"
 #include "sm100_ptx.cuh"
 
 namespace rfa {
@@ -83,7 +84,15 @@ __device__ __forceinline__ bool tile_needs_mask(const SegGeom& g, const WorkItem
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_ks,
+                const __grid_constant__ CUtensorMap tm_vs, const __grid_constant__ FwdParams p) {
+  // The first blocks of the grid are communication CTAs: they push this rank's K/V rows to the peers that
+  // need them while the remaining (compute) CTAs already work on the local shard.
+  if (static_cast<int>(blockIdx.x) < p.push.n_ctas) {
+    push_role(p.push);
+    return;
+  }
+  const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                       // 2 x 32 KB
@@ -92,9 +101,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
+  const int head = cta / p.n_items;  // consecutive CTAs share a head => K/V tiles are reused out of L2
   const int kv_head = head / (p.hq / p.hkv);
-  const WorkItem it = p.items[blockIdx.x];
+  const WorkItem it = p.items[cta % p.n_items];
   const int n_rows0 = it.q_rows < kTile ? it.q_rows : kTile;
   const int n_rows1 = it.q_rows - n_rows0;
   const bool has_t1 = n_rows1 > 0;
@@ -103,6 +112,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_ks);
+    tma_prefetch_desc(&tm_vs);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -123,7 +134,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   if (warp < 4) {
-   reg_dealloc<80>();
+   reg_dealloc<72>();
    if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -139,8 +150,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int si = 0; si < it.seg_count; ++si) {
         const KVSegment sg = p.segs[it.seg_begin + si];
         const SegGeom g = seg_geom(sg, it);
-        if (g.n_tiles > 0 && sg.flag >= 0 && p.ready_flags != nullptr) {
-          wait_flag_ge(p.ready_flags + sg.flag, p.ready_epoch, "fwd kv ready");
+        const bool staged = sg.flag >= 0 && p.ready_flags != nullptr;
+        if (g.n_tiles > 0 && staged) {
+          wait_epoch(p.ready_flags + sg.flag, p.ready_epoch, "fwd kv ready");
           fence_proxy_async_all();
         }
         for (int jj = 0; jj < g.n_tiles; ++jj) {
@@ -148,7 +160,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int kv = 0; kv < 2; ++kv) {
             mbar_wait(&bars->kv_empty[slot], phase ^ 1);
             uint8_t* dst = smem_kv + slot * kTileBytes;
-            const CUtensorMap* tm = kv == 0 ? &tm_k : &tm_v;
+            const CUtensorMap* tm = staged ? (kv == 0 ? &tm_ks : &tm_vs) : (kv == 0 ? &tm_k : &tm_v);
             mbar_arrive_expect_tx(&bars->kv_full[slot], kTileBytes);
             tma_load_3d(dst, tm, &bars->kv_full[slot], 0, kv_head, row);
             tma_load_3d(dst + kHalfBytes, tm, &bars->kv_full[slot], 64, kv_head, row);
@@ -395,29 +407,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+  if (threadIdx.x == 0 && p.sig.world > 0) consumer_done(p.sig);
 }
 
 }  // namespace fwd
 
 const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k, const TensorView& v,
-                            const FwdParams& p, int n_items, cudaStream_t stream) {
-  if (n_items <= 0) return nullptr;
-  CUtensorMap tq, tk, tv;
+                            const TensorView& k_stage, const TensorView& v_stage, const FwdParams& p,
+                            cudaStream_t stream) {
+  const int n_blocks = p.push.n_ctas + p.n_items * p.hq;
+  if (n_blocks <= 0) return nullptr;
+  CUtensorMap tq, tk, tv, tks, tvs;
   if (const char* e = make_tensor_map(&tq, q, 2, fwd::kTile, fwd::kD)) return e;
   if (const char* e = make_tensor_map(&tk, k, 2, fwd::kTile, fwd::kD)) return e;
   if (const char* e = make_tensor_map(&tv, v, 2, fwd::kTile, fwd::kD)) return e;
-  dim3 grid(n_items, p.hq, 1), block(fwd::kThreads, 1, 1);
+  if (const char* e = make_tensor_map(&tks, k_stage, 2, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tvs, v_stage, 2, fwd::kTile, fwd::kD)) return e;
+  dim3 grid(n_blocks, 1, 1), block(fwd::kThreads, 1, 1);
   cudaError_t err;
   if (dtype == kDtypeBF16) {
     auto kern = fwd::attn_fwd_kernel<__nv_bfloat16>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
     if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, p);
+    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
   } else {
     auto kern = fwd::attn_fwd_kernel<__half>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
     if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, p);
+    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
   }
   err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

@@ -26,13 +26,52 @@ TensorView view3(const at::Tensor& t, const char* name) {
 
 void check(const char* err) { TORCH_CHECK(err == nullptr, "ring_flash_attn_b200 kernel launch failed: ", err); }
 
-const uint32_t* flag_ptr(const c10::optional<at::Tensor>& flags) {
-  return flags.has_value() ? reinterpret_cast<const uint32_t*>(flags->data_ptr()) : nullptr;
+// Fused-mode context shared by the forward and backward launches (all lists are indexed by rank).
+struct FusedCtx {
+  at::Tensor k_stage, v_stage;   // (world * rows_cap, hkv, 128) views of this rank's staging buffer (current parity)
+  at::Tensor my_pad;             // int32 view of this rank's signal pad
+  at::Tensor push_tasks;         // int64 (n, 4)
+  at::Tensor counters;           // int32 (64): [0,16) kv sent, [16] done, [32,48) dkv sent, [48] reduce ticket
+  std::vector<int64_t> stage_ptrs, pad_ptrs, sent_targets;
+  int64_t n_push_ctas = 0, row_bytes = 0, my_rank = 0, world = 0, epoch = 0, done_target = 0;
+  // backward only
+  std::vector<int64_t> dk_ptrs, dv_ptrs, dkv_targets;
+  int64_t dkv_wait_epoch = 0;
+};
+
+void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, const at::Tensor& k, const at::Tensor& v) {
+  TORCH_CHECK(c.world <= rfa::kMaxRanks, "too many ranks for the fused path");
+  TORCH_CHECK(c.push_tasks.scalar_type() == at::kLong && c.push_tasks.is_contiguous());
+  TORCH_CHECK(k.stride(1) == 128 && v.stride(1) == 128, "K/V heads must be contiguous inside a row for the push path");
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(c.counters.data_ptr());
+  pp.tasks = reinterpret_cast<const rfa::PushTask*>(c.push_tasks.data_ptr());
+  pp.n_tasks = static_cast<int>(c.push_tasks.size(0));
+  pp.n_ctas = pp.n_tasks > 0 ? static_cast<int>(c.n_push_ctas) : 0;
+  pp.row_bytes = static_cast<int>(c.row_bytes);
+  pp.my_rank = static_cast<int>(c.my_rank);
+  pp.epoch = static_cast<uint32_t>(c.epoch);
+  pp.src_base[0] = static_cast<const char*>(k.data_ptr());
+  pp.src_base[1] = static_cast<const char*>(v.data_ptr());
+  pp.src_row_bytes[0] = k.stride(0) * k.element_size();
+  pp.src_row_bytes[1] = v.stride(0) * v.element_size();
+  pp.my_pad = reinterpret_cast<uint32_t*>(c.my_pad.data_ptr());
+  pp.sent_count = cnt;
+  sg.done_count = cnt + 16;
+  sg.done_target = static_cast<uint32_t>(c.done_target);
+  sg.epoch = static_cast<uint32_t>(c.epoch);
+  sg.world = static_cast<int>(c.world);
+  sg.my_rank = static_cast<int>(c.my_rank);
+  for (int r = 0; r < c.world; ++r) {
+    pp.stage_ptrs[r] = reinterpret_cast<char*>(c.stage_ptrs[r]);
+    pp.peer_pads[r] = reinterpret_cast<uint32_t*>(c.pad_ptrs[r]);
+    pp.sent_target[r] = static_cast<uint32_t>(c.sent_targets[r]);
+    sg.peer_pads[r] = reinterpret_cast<uint32_t*>(c.pad_ptrs[r]);
+  }
 }
 
-void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
-              const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
-              const c10::optional<at::Tensor>& ready_flags, int64_t ready_epoch) {
+void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+                   const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
+                   const FusedCtx* fc) {
   const c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(segs.scalar_type() == at::kInt && segs.is_cuda() && segs.is_contiguous() && segs.size(1) == 4);
@@ -50,10 +89,29 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, con
   p.hkv = static_cast<int>(k.size(1));
   p.scale = static_cast<float>(scale);
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
-  p.ready_flags = flag_ptr(ready_flags);
-  p.ready_epoch = static_cast<uint32_t>(ready_epoch);
-  check(rfa::attn_fwd_launch(dtype_code(q), view3(q, "q"), view3(k, "k"), view3(v, "v"), p,
-                             static_cast<int>(items.size(0)), at::cuda::getCurrentCUDAStream()));
+  p.n_items = static_cast<int>(items.size(0));
+  if (fc != nullptr) {
+    p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
+    p.ready_epoch = static_cast<uint32_t>(fc->epoch);
+    fill_push(p.push, p.sig, *fc, k, v);
+    check(rfa::attn_fwd_launch(dtype_code(q), view3(q, "q"), view3(k, "k"), view3(v, "v"),
+                               view3(fc->k_stage, "k_stage"), view3(fc->v_stage, "v_stage"), p,
+                               at::cuda::getCurrentCUDAStream()));
+  } else {
+    check(rfa::attn_fwd_launch(dtype_code(q), view3(q, "q"), view3(k, "k"), view3(v, "v"), view3(k, "k"),
+                               view3(v, "v"), p, at::cuda::getCurrentCUDAStream()));
+  }
+}
+
+void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+              const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale) {
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr);
+}
+
+void attn_fwd_fused(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+                    const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
+                    const FusedCtx& fc) {
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, &fc);
 }
 
 void attn_bwd_delta(const at::Tensor& out, const at::Tensor& dout, at::Tensor& delta, int64_t lse_S) {
@@ -63,36 +121,97 @@ void attn_bwd_delta(const at::Tensor& out, const at::Tensor& dout, at::Tensor& d
                                    static_cast<int>(lse_S), at::cuda::getCurrentCUDAStream()));
 }
 
-void attn_bwd(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
-              at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
-              const at::Tensor& delta, at::Tensor& dk, at::Tensor& dv, int64_t lse_S, double scale,
-              const c10::optional<at::Tensor>& ready_flags, int64_t ready_epoch) {
+void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
+                   at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
+                   const at::Tensor& delta, const c10::optional<at::Tensor>& dk, const c10::optional<at::Tensor>& dv,
+                   int64_t lse_S, double scale, const FusedCtx* fc) {
   const c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(qsegs.scalar_type() == at::kInt && qsegs.is_cuda() && qsegs.is_contiguous() && qsegs.size(1) == 4);
   TORCH_CHECK(dq_accum.scalar_type() == at::kFloat && dq_accum.dim() == 3 && dq_accum.size(2) == 128 &&
               dq_accum.stride(2) == 1);
-  TORCH_CHECK(dk.scalar_type() == at::kFloat && dk.is_contiguous() && dv.scalar_type() == at::kFloat &&
-              dv.is_contiguous());
+  if (fc == nullptr) {
+    TORCH_CHECK(dk.has_value() && dv.has_value());
+    TORCH_CHECK(dk->scalar_type() == at::kFloat && dk->is_contiguous() && dv->scalar_type() == at::kFloat &&
+                dv->is_contiguous());
+  }
   TORCH_CHECK(lse.scalar_type() == at::kFloat && delta.scalar_type() == at::kFloat);
   rfa::BwdParams p{};
   p.items = reinterpret_cast<const rfa::BwdItem*>(items.data_ptr());
   p.qsegs = reinterpret_cast<const rfa::BwdQSegment*>(qsegs.data_ptr());
   p.lse = lse.data_ptr<float>();
   p.delta = delta.data_ptr<float>();
-  p.dk = dk.data_ptr<float>();
-  p.dv = dv.data_ptr<float>();
+  p.dk = dk.has_value() ? dk->data_ptr<float>() : nullptr;
+  p.dv = dv.has_value() ? dv->data_ptr<float>() : nullptr;
   p.lse_S = static_cast<int>(lse_S);
   p.hq = static_cast<int>(q.size(1));
   p.hkv = static_cast<int>(k.size(1));
   p.scale = static_cast<float>(scale);
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
-  p.ready_flags = flag_ptr(ready_flags);
-  p.ready_epoch = static_cast<uint32_t>(ready_epoch);
   TensorView dqv{dq_accum.data_ptr(), dq_accum.size(0), static_cast<int>(dq_accum.size(1)), dq_accum.stride(0),
                  dq_accum.stride(1)};
-  check(rfa::attn_bwd_launch(dtype_code(q), view3(q, "q"), view3(dout, "dout"), view3(k, "k"), view3(v, "v"), dqv, p,
-                             static_cast<int>(items.size(0)), at::cuda::getCurrentCUDAStream()));
+  p.n_items = static_cast<int>(items.size(0));
+  if (fc != nullptr) {
+    p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
+    p.ready_epoch = static_cast<uint32_t>(fc->epoch);
+    fill_push(p.push, p.sig, *fc, k, v);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(fc->counters.data_ptr());
+    p.dkv.my_pad = reinterpret_cast<uint32_t*>(fc->my_pad.data_ptr());
+    p.dkv.sent_count = cnt + 32;
+    p.dkv.epoch = static_cast<uint32_t>(fc->epoch);
+    p.dkv.wait_epoch = static_cast<uint32_t>(fc->dkv_wait_epoch);
+    p.dkv.world = static_cast<int>(fc->world);
+    p.dkv.my_rank = static_cast<int>(fc->my_rank);
+    for (int r = 0; r < fc->world; ++r) {
+      p.dkv.dk_ptrs[r] = reinterpret_cast<float*>(fc->dk_ptrs[r]);
+      p.dkv.dv_ptrs[r] = reinterpret_cast<float*>(fc->dv_ptrs[r]);
+      p.dkv.peer_pads[r] = reinterpret_cast<uint32_t*>(fc->pad_ptrs[r]);
+      p.dkv.sent_target[r] = static_cast<uint32_t>(fc->dkv_targets[r]);
+    }
+    check(rfa::attn_bwd_launch(dtype_code(q), view3(q, "q"), view3(dout, "dout"), view3(k, "k"), view3(v, "v"),
+                               view3(fc->k_stage, "k_stage"), view3(fc->v_stage, "v_stage"), dqv, p,
+                               at::cuda::getCurrentCUDAStream()));
+  } else {
+    check(rfa::attn_bwd_launch(dtype_code(q), view3(q, "q"), view3(dout, "dout"), view3(k, "k"), view3(v, "v"),
+                               view3(k, "k"), view3(v, "v"), dqv, p, at::cuda::getCurrentCUDAStream()));
+  }
+}
+
+void attn_bwd(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
+              at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
+              const at::Tensor& delta, at::Tensor& dk, at::Tensor& dv, int64_t lse_S, double scale) {
+  attn_bwd_impl(q, dout, k, v, dq_accum, items, qsegs, lse, delta, dk, dv, lse_S, scale, nullptr);
+}
+
+void attn_bwd_fused(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
+                    at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
+                    const at::Tensor& delta, int64_t lse_S, double scale, const FusedCtx& fc) {
+  attn_bwd_impl(q, dout, k, v, dq_accum, items, qsegs, lse, delta, c10::nullopt, c10::nullopt, lse_S, scale, &fc);
+}
+
+// Owner-side reduction of the dK/dV inbox (csrc/comm_sm100.cu).
+void reduce_dkv(const at::Tensor& inbox, int64_t slot_stride, int64_t kv_stride, at::Tensor& dk, at::Tensor& dv,
+                const at::Tensor& tasks, const FusedCtx& fc, int64_t ticket_target) {
+  const c10::cuda::CUDAGuard guard(inbox.device());
+  TORCH_CHECK(inbox.scalar_type() == at::kFloat && dk.is_contiguous() && dv.is_contiguous());
+  TORCH_CHECK(tasks.scalar_type() == at::kInt && tasks.is_contiguous() && tasks.size(1) == 4);
+  rfa::ReduceParams p{};
+  p.tasks = reinterpret_cast<const rfa::ReduceTask*>(tasks.data_ptr());
+  p.n_tasks = static_cast<int>(tasks.size(0));
+  p.inbox = inbox.data_ptr<float>();
+  p.slot_stride = slot_stride;
+  p.kv_stride = kv_stride;
+  p.dk = dk.data_ptr();
+  p.dv = dv.data_ptr();
+  p.row_elems = static_cast<int>(dk.size(1) * dk.size(2));
+  p.my_pad = reinterpret_cast<const uint32_t*>(fc.my_pad.data_ptr());
+  p.ticket = reinterpret_cast<uint32_t*>(fc.counters.data_ptr()) + 48;
+  p.ticket_target = static_cast<uint32_t>(ticket_target);
+  p.epoch = static_cast<uint32_t>(fc.epoch);
+  p.world = static_cast<int>(fc.world);
+  p.my_rank = static_cast<int>(fc.my_rank);
+  for (int r = 0; r < fc.world; ++r) p.peer_pads[r] = reinterpret_cast<uint32_t*>(fc.pad_ptrs[r]);
+  check(rfa::reduce_dkv_launch(dtype_code(dk), p, at::cuda::getCurrentCUDAStream()));
 }
 
 at::Tensor probe(const at::Tensor& a, const at::Tensor& b, std::vector<int64_t> cfg) {
@@ -143,7 +262,30 @@ at::Tensor lse_unflatten(const at::Tensor& lse, const at::Tensor& cu, int64_t ma
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "ring_flash_attn_b200 sm_100a kernels";
+  pybind11::class_<FusedCtx>(m, "FusedCtx")
+      .def(pybind11::init<>())
+      .def_readwrite("k_stage", &FusedCtx::k_stage)
+      .def_readwrite("v_stage", &FusedCtx::v_stage)
+      .def_readwrite("my_pad", &FusedCtx::my_pad)
+      .def_readwrite("push_tasks", &FusedCtx::push_tasks)
+      .def_readwrite("counters", &FusedCtx::counters)
+      .def_readwrite("stage_ptrs", &FusedCtx::stage_ptrs)
+      .def_readwrite("pad_ptrs", &FusedCtx::pad_ptrs)
+      .def_readwrite("sent_targets", &FusedCtx::sent_targets)
+      .def_readwrite("n_push_ctas", &FusedCtx::n_push_ctas)
+      .def_readwrite("row_bytes", &FusedCtx::row_bytes)
+      .def_readwrite("my_rank", &FusedCtx::my_rank)
+      .def_readwrite("world", &FusedCtx::world)
+      .def_readwrite("epoch", &FusedCtx::epoch)
+      .def_readwrite("done_target", &FusedCtx::done_target)
+      .def_readwrite("dk_ptrs", &FusedCtx::dk_ptrs)
+      .def_readwrite("dv_ptrs", &FusedCtx::dv_ptrs)
+      .def_readwrite("dkv_targets", &FusedCtx::dkv_targets)
+      .def_readwrite("dkv_wait_epoch", &FusedCtx::dkv_wait_epoch);
   m.def("attn_fwd", &attn_fwd);
+  m.def("attn_fwd_fused", &attn_fwd_fused);
+  m.def("attn_bwd_fused", &attn_bwd_fused);
+  m.def("reduce_dkv", &reduce_dkv);
   m.def("attn_bwd_delta", &attn_bwd_delta);
   m.def("attn_bwd", &attn_bwd);
   m.def("probe", &probe);

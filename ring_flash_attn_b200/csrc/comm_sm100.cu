@@ -1,0 +1,88 @@
+// Owner-side reduction of the backward "inbox".
+//
+// During the fused backward every rank stores its fp32 dK/dV partials for a shard directly into the shard
+// owner's inbox slot over NVLink (attn_bwd_sm100.cu epilogue).  This kernel runs on the owner afterwards:
+// it waits until every contributing rank has raised its "gradients landed" epoch, sums the slots that hold a
+// partial for each row range in a fixed order (so the result is deterministic), writes dK/dV in the model
+// dtype and finally tells every peer that the inbox may be reused.  It replaces the reference's W-hop fp32
+// dK/dV ring (/root/reference/ring_flash_attn/ring_flash_attn.py:139-152) and llama3's blocking
+// reduce_scatter (llama3_flash_attn_varlen.py:292-293).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "attn_common.h"
+#include "comm_device.cuh"
+
+namespace rfa {
+namespace comm {
+
+template <typename T>
+__device__ __forceinline__ uint2 pack4(const float4& a);
+template <>
+__device__ __forceinline__ uint2 pack4<__nv_bfloat16>(const float4& a) {
+  return make_uint2(Pack2<__nv_bfloat16>::pack(a.x, a.y), Pack2<__nv_bfloat16>::pack(a.z, a.w));
+}
+template <>
+__device__ __forceinline__ uint2 pack4<__half>(const float4& a) {
+  return make_uint2(Pack2<__half>::pack(a.x, a.y), Pack2<__half>::pack(a.z, a.w));
+}
+
+// grid: (blocks_per_task, n_tasks)
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__ ReduceParams p) {
+  const ReduceTask t = p.tasks[blockIdx.y];
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < p.world; ++r) {
+      if ((t.src_mask >> r) & 1u) {
+        if (r != p.my_rank) wait_epoch(p.my_pad + kPadDkvReady + r, p.epoch, "dkv landed");
+      }
+    }
+  }
+  __syncthreads();
+  const long long n4 = static_cast<long long>(t.rows) * p.row_elems / 4;
+  const long long off4 = static_cast<long long>(t.row0) * p.row_elems / 4;
+  for (int which = 0; which < 2; ++which) {
+    const float4* in = reinterpret_cast<const float4*>(p.inbox + which * p.kv_stride) + off4;
+    uint2* out = reinterpret_cast<uint2*>(which == 0 ? p.dk : p.dv) + off4;
+    const long long slot4 = p.slot_stride / 4;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < p.world; ++r) {
+        if ((t.src_mask >> r) & 1u) {
+          const float4 v = __ldcv(in + r * slot4 + i);  // written by a peer: never serve it from a stale line
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+      }
+      out[i] = pack4<T>(acc);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t old = atomicAdd(p.ticket, 1u);
+    if (old + 1u == p.ticket_target) {
+      __threadfence_system();
+      for (int r = 0; r < p.world; ++r) st_release_sys(p.peer_pads[r] + kPadInboxFree + p.my_rank, p.epoch);
+    }
+  }
+}
+
+}  // namespace comm
+
+const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream) {
+  if (p.n_tasks <= 0) return nullptr;
+  dim3 grid(16, p.n_tasks, 1);
+  if (dtype == kDtypeBF16) {
+    comm::reduce_dkv_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
+  } else {
+    comm::reduce_dkv_kernel<__half><<<grid, 256, 0, stream>>>(p);
+  }
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+}  // namespace rfa

@@ -135,7 +135,7 @@ def _rows3(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None, ready_flags=None, ready_epoch=0):
+def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None):
     """Run the forward kernel over prepared tables.  Returns (out (Tq,Hq,128) in q.dtype, lse (Hq,Tq) fp32)."""
     C = cuda_ext.load()
     tq, hq, d = q.shape
@@ -146,8 +146,7 @@ def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None, rea
         if not covered:
             lse.fill_(float("-inf"))
     if items.shape[0]:
-        C.attn_fwd(_rows3(q), _rows3(k), _rows3(v), items, segs, out, lse, tq, float(scale), ready_flags,
-                   int(ready_epoch))
+        C.attn_fwd(_rows3(q), _rows3(k), _rows3(v), items, segs, out, lse, tq, float(scale))
         cuda_ext.note_launch()
     return out, lse
 
@@ -168,12 +167,11 @@ def compute_delta(out, dout, hq_rows=None) -> torch.Tensor:
     return delta
 
 
-def backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq_accum, dk, dv, ready_flags=None,
-                    ready_epoch=0):
+def backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq_accum, dk, dv):
     C = cuda_ext.load()
     if items.shape[0]:
         C.attn_bwd(_rows3(q), _rows3(dout), _rows3(k), _rows3(v), dq_accum, items, qsegs, lse, delta, dk, dv,
-                   q.shape[0], float(scale), ready_flags, int(ready_epoch))
+                   q.shape[0], float(scale))
         cuda_ext.note_launch()
 
 
