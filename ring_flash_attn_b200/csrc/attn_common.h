@@ -47,8 +47,8 @@ constexpr int kPadWords = 1024;
 // One contiguous run of K (or V) rows to copy from local memory into a peer's staging buffer.
 // Offsets (not pointers) so that the table depends only on the plan and can be cached on the device.
 struct alignas(16) PushTask {
-  long long src_off;  // bytes from the local K (which == 0) or V (which == 1) base to the first row
-  long long dst_off;  // bytes from the destination's staging base to the first staged row
+  long long src_row;  // first local row of K (which == 0) or V (which == 1)
+  long long dst_off;  // bytes from the destination's staging base (current parity) to the first staged row
   int rows;
   int dst;    // destination rank
   int which;  // 0 = K, 1 = V
@@ -62,6 +62,7 @@ struct PushParams {
   int row_bytes;  // bytes per staged row (kv heads * 128 * 2)
   int my_rank;
   uint32_t epoch;
+  long long parity_off;         // byte offset of the staging half used by this call
   const char* src_base[2];      // local K / V
   long long src_row_bytes[2];   // local row pitch of K / V
   char* stage_ptrs[kMaxRanks];  // peer-mapped staging base of every rank

@@ -33,7 +33,7 @@ struct FusedCtx {
   at::Tensor push_tasks;         // int64 (n, 4)
   at::Tensor counters;           // int32 (64): [0,16) kv sent, [16] done, [32,48) dkv sent, [48] reduce ticket
   std::vector<int64_t> stage_ptrs, pad_ptrs, sent_targets;
-  int64_t n_push_ctas = 0, row_bytes = 0, my_rank = 0, world = 0, epoch = 0, done_target = 0;
+  int64_t n_push_ctas = 0, row_bytes = 0, my_rank = 0, world = 0, epoch = 0, done_target = 0, parity_off = 0;
   // backward only
   std::vector<int64_t> dk_ptrs, dv_ptrs, dkv_targets;
   int64_t dkv_wait_epoch = 0;
@@ -50,6 +50,7 @@ void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, co
   pp.row_bytes = static_cast<int>(c.row_bytes);
   pp.my_rank = static_cast<int>(c.my_rank);
   pp.epoch = static_cast<uint32_t>(c.epoch);
+  pp.parity_off = c.parity_off;
   pp.src_base[0] = static_cast<const char*>(k.data_ptr());
   pp.src_base[1] = static_cast<const char*>(v.data_ptr());
   pp.src_row_bytes[0] = k.stride(0) * k.element_size();
@@ -278,6 +279,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("world", &FusedCtx::world)
       .def_readwrite("epoch", &FusedCtx::epoch)
       .def_readwrite("done_target", &FusedCtx::done_target)
+      .def_readwrite("parity_off", &FusedCtx::parity_off)
       .def_readwrite("dk_ptrs", &FusedCtx::dk_ptrs)
       .def_readwrite("dv_ptrs", &FusedCtx::dv_ptrs)
       .def_readwrite("dkv_targets", &FusedCtx::dkv_targets)

@@ -58,9 +58,9 @@ __device__ __forceinline__ void push_role(const PushParams& pp) {
     __syncthreads();
     const int vec_per_row = pp.row_bytes >> 4;
     const long long total = static_cast<long long>(t.rows) * vec_per_row;
-    const char* src = pp.src_base[t.which] + t.src_off;
-    char* dst = pp.stage_ptrs[t.dst] + t.dst_off;
     const long long src_pitch = pp.src_row_bytes[t.which];
+    const char* src = pp.src_base[t.which] + t.src_row * src_pitch;
+    char* dst = pp.stage_ptrs[t.dst] + pp.parity_off + t.dst_off;
     constexpr int U = 8;
     for (long long base = static_cast<long long>(tid); base < total; base += static_cast<long long>(nthr) * U) {
       uint4 v[U];

@@ -11,8 +11,9 @@
 namespace rfa {
 
 #ifndef RFA_WATCHDOG_NS
-// Bounded waits turn a protocol bug into a trap (an error) instead of a hung GPU: 4 s of wall time.
-#define RFA_WATCHDOG_NS 4000000000ull
+// Bounded waits turn a protocol bug into a trap (an error) instead of a hung GPU: 20 s of wall time
+// (cross-GPU waits must tolerate a peer that is late by a lazy module load or a host hiccup).
+#define RFA_WATCHDOG_NS 20000000000ull
 #endif
 
 __device__ __forceinline__ uint64_t global_timer_ns() {

@@ -91,6 +91,45 @@ def bwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int,
     return [it for _, it in items], qsegs
 
 
+def bwd_tables_fused(plan: CPPlan, row_offset: Dict[int, int], device, flag_of_src: Dict[int, int]):
+    """Backward tables for the fused multi-GPU launch: every key tile carries its owner rank and its row
+    inside the owner's shard; tiles that no local query reaches are still emitted (they store zeros into
+    the owner's inbox so that the owner-side reduction never reads stale memory).  Cached on the plan."""
+    c = _cache(plan)
+    key = ("bwd_fused", device.index)
+    if key in c:
+        return c[key]
+    by_src: Dict[int, List[Segment]] = {}
+    for s in plan.segments:
+        by_src.setdefault(s.src, []).append(s)
+    items, qsegs = [], []
+    per_owner = [0] * plan.world
+    for src, ss in by_src.items():
+        cuts = sorted({s.kv_row0 for s in ss} | {s.kv_row0 + s.kv_len for s in ss})
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            cover = [s for s in ss if s.kv_row0 <= lo and s.kv_row0 + s.kv_len >= hi]
+            if not cover:
+                continue
+            for t0 in range(lo, hi, K_TILE_ROWS):
+                rows = min(K_TILE_ROWS, hi - t0)
+                begin = len(qsegs)
+                work = 0
+                for s in cover:
+                    ch = plan.q_chunks[s.chunk]
+                    d = DIAG_FULL if s.diag is None else s.diag - (t0 - s.kv_row0)
+                    if ch.rows - 1 + d < 0:
+                        continue
+                    qsegs.append([ch.row0, ch.rows, d, 0])
+                    work += ch.rows - max(0, -d)
+                flag = flag_of_src.get(src, -1)
+                items.append((work, [row_offset[src] + t0, rows, begin, len(qsegs) - begin, flag, src, t0, 0]))
+                per_owner[src] += 1
+    items.sort(key=lambda t: -t[0])
+    c[key] = (_to_dev([it for _, it in items], 8, device), _to_dev(qsegs if qsegs else [[0, 0, 0, 0]], 4, device),
+              per_owner)
+    return c[key]
+
+
 def _to_dev(rows: List[List[int]], width: int, device) -> torch.Tensor:
     if not rows:
         return torch.zeros((0, width), dtype=torch.int32, device=device)

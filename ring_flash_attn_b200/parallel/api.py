@@ -71,6 +71,9 @@ def _scale(q, softmax_scale):
 
 
 _CU_CACHE = {}
+# (cu_q, cu_k, k_start, rank, world, causal) -> global cu_seqlens, filled by prepare(); lets a rank derive its
+# peers' llama3 plans locally (needed by the fused path to know which K/V rows each peer wants).
+_LLAMA3_GLOBAL = {}
 
 
 def cu_seqlens_to_host(cu: torch.Tensor) -> Tuple[int, ...]:
@@ -122,6 +125,7 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
     rank, world = group_info(group)
     b, s, hq, d = q.shape
     plan = _batch_plan(scheme, rank, world, b, s, bool(causal))
+    plan.peer = lambda r, _a=(scheme, world, b, s, bool(causal)): _batch_plan(_a[0], r, *_a[1:])
     out, lse = CPAttention.apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
                                  v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
                                  "ring", 1, deterministic)
@@ -137,7 +141,9 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
     if scheme == "zigzag" and not causal:
         raise AssertionError("zigzag attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
-    plan = _varlen_plan(scheme, rank, world, cu_seqlens_to_host(cu_seqlens), bool(causal))
+    cu_host = cu_seqlens_to_host(cu_seqlens)
+    plan = _varlen_plan(scheme, rank, world, cu_host, bool(causal))
+    plan.peer = lambda r, _a=(scheme, world, cu_host, bool(causal)): _varlen_plan(_a[0], r, *_a[1:])
     if plan.q_rows != q.shape[0]:
         raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
     out, lse = CPAttention.apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic)
@@ -252,9 +258,19 @@ def llama3_flash_attn_prepare_cu_seqlens(cu_seqlens: torch.Tensor, causal: bool,
     cu_k_t = torch.tensor(cu_k, dtype=dt, device=dev)
     _CU_CACHE[(cu_q_t.data_ptr(), cu_q_t._version, cu_q_t.numel(), cu_q_t.device.index)] = tuple(cu_q)
     _CU_CACHE[(cu_k_t.data_ptr(), cu_k_t._version, cu_k_t.numel(), cu_k_t.device.index)] = tuple(cu_k)
+    if len(_LLAMA3_GLOBAL) > 1024:
+        _LLAMA3_GLOBAL.clear()
+    _LLAMA3_GLOBAL[(tuple(cu_q), tuple(cu_k), slice_left, rank, world_size, bool(causal))] = tuple(cu)
     max_q = max(b - a for a, b in zip(cu_q[:-1], cu_q[1:]))
     max_k = max(b - a for a, b in zip(cu_k[:-1], cu_k[1:]))
     return cu_q_t, cu_k_t, max_q, max_k, slice(slice_left, slice_right)
+
+
+@functools.lru_cache(maxsize=512)
+def _llama3_peer_plan(global_cu, causal, rank, world, tokens):
+    cq, ck, _mq, _mk, ks = llama3_flash_attn_prepare_cu_seqlens(torch.tensor(global_cu, dtype=torch.int32), causal,
+                                                               rank, world)
+    return _llama3_plan(rank, world, tokens, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), causal)
 
 
 def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
@@ -266,8 +282,11 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
     _check_common(q, dropout_p, window_size, alibi_slopes)
     rank, world = group_info(group)
     k_start = local_k_slice.start or 0
-    plan = _llama3_plan(rank, world, q.shape[0], cu_seqlens_to_host(cu_seqlens_q),
-                        cu_seqlens_to_host(cu_seqlens_k), int(k_start), bool(causal))
+    cu_q_host, cu_k_host = cu_seqlens_to_host(cu_seqlens_q), cu_seqlens_to_host(cu_seqlens_k)
+    plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal))
+    glob = _LLAMA3_GLOBAL.get((cu_q_host, cu_k_host, int(k_start), rank, world, bool(causal)))
+    if glob is not None:
+        plan.peer = lambda r, _g=glob, _w=world, _c=bool(causal), _t=q.shape[0]: _llama3_peer_plan(_g, _c, r, _w, _t)
     out, lse = CPAttention.apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
                                  int(heads_k_stride), deterministic)
     return (out, lse, None) if return_attn_probs else out

@@ -1,6 +1,319 @@
-"""Peer-memory context (placeholder until the NVLink path lands): reports "unavailable" so multi-GPU calls
-use the torch.distributed transport around the sm_100a block kernels."""
+"""Peer-memory runtime and the fused multi-GPU forward / backward drivers.
+
+One :class:`PeerContext` exists per (process group, device).  It owns three CUDA-IPC buffers that every
+rank of the group maps (``csrc/peer_mem.cpp``):
+
+* the *signal pad*   - uint32 epochs written by peers (layout in ``csrc/attn_common.h``: kPad*),
+* the *K/V staging*  - ``[parity][K|V][slot = source rank][rows][hkv][128]``: the rows of every other rank's
+                       shard that this rank's plan needs, stored there by the *source's* attention kernel,
+* the *dK/dV inbox*  - ``[slot = source rank][dK|dV][rows][hkv][128]`` fp32: partial gradients for this
+                       rank's shard, stored there by the peers' backward kernels.
+
+A forward is ONE launch of ``attn_fwd_kernel``: its first CTAs push this rank's K/V rows to the peers that
+need them (ring order, posted NVLink stores), the rest run the math and only wait on a source's "landed"
+flag when they reach that source's segments.  A backward is ``delta`` + ONE launch of ``attn_bwd_kernel``
+(same push CTAs; dK/dV tiles are stored straight into the owners' inboxes) + the owner-side reduction.
+No NCCL call is on these paths; NCCL is used once, to exchange the IPC handles.
+
+Replaces: RingComm.send_recv_kv / batch_isend_irecv, all_gather_into_tensor and reduce_scatter_tensor in
+/root/reference/ring_flash_attn/utils.py:98-168 and llama3_flash_attn_varlen.py:97-115,292-293.
+"""
+from __future__ import annotations
+
+import os
+import socket
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import attn_cuda, cuda_ext
+from ..ops.plan import CPPlan
+from .comm import group_info
+
+PAD_WORDS = 1024
+MASK32 = 0xFFFFFFFF
+_CONTEXTS: Dict[Tuple[int, int], Optional["PeerContext"]] = {}
 
 
-def peer_context(group, device):
-    return None
+class PeerBuffer:
+    """A cudaMalloc'd buffer mapped by every rank of the group."""
+
+    def __init__(self, nbytes: int, device: torch.device, group):
+        C = cuda_ext.load()
+        self.nbytes = nbytes
+        self.device = device
+        self.local_ptr, handle = C.peer_alloc(int(nbytes), device.index)
+        rank, world = group_info(group)
+        handles: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(handles, (device.index, handle), group=group)
+        self.ptrs: List[int] = []
+        for r, (_dev, h) in enumerate(handles):
+            self.ptrs.append(self.local_ptr if r == rank else C.peer_open(h, device.index))
+        self.rank = rank
+
+    def tensor(self, byte_offset: int, shape, dtype) -> torch.Tensor:
+        return cuda_ext.load().tensor_from_ptr(self.local_ptr + byte_offset, list(shape), dtype, self.device.index)
+
+    def close(self):
+        C = cuda_ext.load()
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                C.peer_close(p)
+        C.peer_free(self.local_ptr)
+        self.ptrs = []
+
+
+class PeerContext:
+    def __init__(self, group, device: torch.device):
+        self.group = group
+        self.device = device
+        self.rank, self.world = group_info(group)
+        self.pad = PeerBuffer(PAD_WORDS * 4, device, group)
+        self.pad_tensor = self.pad.tensor(0, (PAD_WORDS,), torch.int32)
+        self.counters = torch.zeros(64, dtype=torch.int32, device=device)
+        self.epoch = 0
+        self.last_bwd_epoch = 0
+        self.sent_cum = [0] * self.world
+        self.dkv_cum = [0] * self.world
+        self.done_cum = 0
+        self.ticket_cum = 0
+        self.stage: Optional[PeerBuffer] = None
+        self.stage_key = None
+        self.inbox: Optional[PeerBuffer] = None
+        self.inbox_key = None
+        self.n_push_ctas = int(os.environ.get("RFA_B200_PUSH_CTAS", "8"))
+
+    # -- buffers ------------------------------------------------------------------------------------
+    def _quiesce(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def ensure_stage(self, rows: int, hkv: int, dtype) -> None:
+        esize = torch.empty((), dtype=dtype).element_size()
+        key = (rows, hkv, esize)
+        if self.stage_key == key:
+            return
+        self._quiesce()
+        if self.stage is not None:
+            self.stage.close()
+        row_bytes = hkv * 128 * esize
+        self.stage_half = 2 * self.world * rows * row_bytes  # one parity: [K|V][slot][rows]
+        self.stage = PeerBuffer(2 * self.stage_half, self.device, self.group)
+        self.stage_key = key
+        self._quiesce()
+
+    def ensure_inbox(self, rows: int, hkv: int) -> None:
+        key = (rows, hkv)
+        if self.inbox_key == key:
+            return
+        self._quiesce()
+        if self.inbox is not None:
+            self.inbox.close()
+        self.inbox_kv_stride = rows * hkv * 128  # floats
+        self.inbox_slot_stride = 2 * self.inbox_kv_stride
+        self.inbox = PeerBuffer(self.world * self.inbox_slot_stride * 4, self.device, self.group)
+        self.inbox_key = key
+        self._quiesce()
+
+    # -- per-call context object --------------------------------------------------------------------
+    def fused_ctx(self, plan: CPPlan, k: torch.Tensor, n_compute_ctas: int):
+        C = cuda_ext.load()
+        rows, hkv = plan.kv_rows, k.shape[1]
+        esize = k.element_size()
+        row_bytes = hkv * 128 * esize
+        self.epoch += 1
+        parity = self.epoch & 1
+        fc = C.FusedCtx()
+        half = parity * self.stage_half
+        region = self.world * rows * row_bytes
+        fc.k_stage = self.stage.tensor(half, (self.world * rows, hkv, 128), k.dtype)
+        fc.v_stage = self.stage.tensor(half + region, (self.world * rows, hkv, 128), k.dtype)
+        fc.my_pad = self.pad_tensor
+        tasks, per_dst = push_tasks(plan, self, row_bytes, k.device)
+        fc.push_tasks = tasks
+        fc.counters = self.counters
+        fc.stage_ptrs = list(self.stage.ptrs)
+        fc.pad_ptrs = list(self.pad.ptrs)
+        for d in range(self.world):
+            self.sent_cum[d] = (self.sent_cum[d] + per_dst[d]) & MASK32
+        fc.sent_targets = list(self.sent_cum)
+        fc.n_push_ctas = min(self.n_push_ctas, int(tasks.shape[0])) if tasks.shape[0] else 0
+        fc.row_bytes = row_bytes
+        fc.my_rank = self.rank
+        fc.world = self.world
+        fc.epoch = self.epoch
+        fc.parity_off = half
+        self.done_cum = (self.done_cum + n_compute_ctas) & MASK32
+        fc.done_target = self.done_cum
+        return fc
+
+
+def peer_context(group, device: torch.device) -> Optional[PeerContext]:
+    """The context for (group, device), created collectively on first use; None if P2P is unavailable."""
+    key = (id(group) if group is not None else 0, device.index)
+    if key in _CONTEXTS:
+        return _CONTEXTS[key]
+    rank, world = group_info(group)
+    C = cuda_ext.load()
+    info: List[Optional[tuple]] = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), device.index), group=group)
+    ok = len({h for h, _ in info}) == 1 and len({d for _, d in info}) == world and world <= 16
+    if ok:
+        ok = all(d == device.index or C.can_access_peer(device.index, d) for _, d in info)
+    flags: List[Optional[bool]] = [None] * world
+    dist.all_gather_object(flags, bool(ok), group=group)
+    ctx = PeerContext(group, device) if all(flags) else None
+    _CONTEXTS[key] = ctx
+    return ctx
+
+
+# ----------------------------------------------------------------------------------------------
+# who needs what
+# ----------------------------------------------------------------------------------------------
+
+def needs_matrix(plan: CPPlan, group) -> List[List[List[Tuple[int, int]]]]:
+    """needs[dst][src] = list of [lo, hi) row ranges of src's shard that dst's plan reads.
+
+    Derived locally from the plan family when the scheme is position-based; exchanged once over the
+    process group otherwise (llama3 layouts whose global cu_seqlens this rank never saw)."""
+    cached = getattr(plan, "_needs", None)
+    if cached is not None:
+        return cached
+    world = plan.world
+    peer = getattr(plan, "peer", None)
+    if peer is not None:
+        fam = [plan if r == plan.rank else peer(r) for r in range(world)]
+        needs = [[_ranges(fam[d], s) for s in range(world)] for d in range(world)]
+    else:
+        mine = [_ranges(plan, s) for s in range(world)]
+        gathered: List[Optional[list]] = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        needs = gathered
+    plan._needs = needs
+    return needs
+
+
+def _ranges(plan: CPPlan, src: int) -> List[Tuple[int, int]]:
+    iv = sorted((s.kv_row0, s.kv_row0 + s.kv_len) for s in plan.segments if s.src == src)
+    out: List[Tuple[int, int]] = []
+    for lo, hi in iv:
+        if out and lo <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], hi))
+        else:
+            out.append((lo, hi))
+    return out
+
+
+def push_tasks(plan: CPPlan, ctx: PeerContext, row_bytes: int, device):
+    """(int64 task table on the device, tasks per destination).  Cached on the plan."""
+    key = ("push", row_bytes, device.index)
+    cache = attn_cuda._cache(plan)
+    if key in cache:
+        return cache[key]
+    needs = needs_matrix(plan, ctx.group)
+    me, world, rows = plan.rank, plan.world, plan.kv_rows
+    chunk = max(16, (1 << 19) // row_bytes)  # ~512 KB per task
+    region = world * rows * row_bytes
+    table, per_dst = [], [0] * world
+    for step in range(1, world):
+        dst = (me + step) % world  # ring order: the next neighbour consumes our shard first
+        for lo, hi in needs[dst][me]:
+            for r0 in range(lo, hi, chunk):
+                n = min(chunk, hi - r0)
+                for which in (0, 1):
+                    dst_off = which * region + (me * rows + r0) * row_bytes
+                    table.append([r0, dst_off, n | (dst << 32), which])
+                    per_dst[dst] += 1
+    t = torch.tensor(table, dtype=torch.int64).to(device) if table else torch.zeros((0, 4), dtype=torch.int64,
+                                                                                     device=device)
+    cache[key] = (t, per_dst)
+    return cache[key]
+
+
+# ----------------------------------------------------------------------------------------------
+# fused forward / backward
+# ----------------------------------------------------------------------------------------------
+
+def _kv_ok(t: torch.Tensor) -> torch.Tensor:
+    t = attn_cuda._rows3(t)
+    return t if t.stride(1) == 128 else t.contiguous()
+
+
+def fused_forward(plan: CPPlan, q, k, v, scale, group):
+    ctx = peer_context(group, q.device)
+    C = cuda_ext.load()
+    k, v = _kv_ok(k), _kv_ok(v)
+    rows, hq = plan.kv_rows, q.shape[1]
+    ctx.ensure_stage(rows, k.shape[1], k.dtype)
+    offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
+    flags = {s: s for s in range(plan.world) if s != plan.rank}
+    items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, offsets, q.device, ("fused",), flags)
+    fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hq)
+    tq = q.shape[0]
+    out = (torch.empty if covered else torch.zeros)((tq, hq, 128), dtype=q.dtype, device=q.device)
+    lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
+    if not covered:
+        lse.fill_(float("-inf"))
+    C.attn_fwd_fused(attn_cuda._rows3(q), k, v, items, segs, out, lse, tq, float(scale), fc)
+    cuda_ext.note_launch()
+    return out, lse
+
+
+def reduce_tasks(plan: CPPlan, ctx: PeerContext, device):
+    key = ("reduce", device.index)
+    cache = attn_cuda._cache(plan)
+    if key in cache:
+        return cache[key]
+    needs = needs_matrix(plan, ctx.group)
+    me, world, rows = plan.rank, plan.world, plan.kv_rows
+    cuts = {0, rows}
+    for s in range(world):
+        for lo, hi in needs[s][me]:
+            cuts.update((lo, hi))
+    cuts = sorted(cuts)
+    table = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        mask = 0
+        for s in range(world):
+            if any(a <= lo and hi <= b for a, b in needs[s][me]):
+                mask |= 1 << s
+        table.append([lo, hi - lo, mask, 0])
+    t = torch.tensor(table, dtype=torch.int32).to(device)
+    cache[key] = t
+    return t
+
+
+def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, deterministic=False):
+    ctx = peer_context(group, q.device)
+    C = cuda_ext.load()
+    k, v = _kv_ok(k), _kv_ok(v)
+    rows, hkv = plan.kv_rows, k.shape[1]
+    ctx.ensure_stage(rows, hkv, k.dtype)
+    ctx.ensure_inbox(rows, hkv)
+    offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
+    flags = {s: s for s in range(plan.world) if s != plan.rank}
+    items, qsegs, per_owner = attn_cuda.bwd_tables_fused(plan, offsets, q.device, flags)
+    delta = attn_cuda.compute_delta(out, dout)
+    dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hkv)
+    me = plan.rank
+    fc.dk_ptrs = [p + me * ctx.inbox_slot_stride * 4 for p in ctx.inbox.ptrs]
+    fc.dv_ptrs = [p + (me * ctx.inbox_slot_stride + ctx.inbox_kv_stride) * 4 for p in ctx.inbox.ptrs]
+    for o in range(plan.world):
+        ctx.dkv_cum[o] = (ctx.dkv_cum[o] + per_owner[o] * hkv) & MASK32
+    fc.dkv_targets = list(ctx.dkv_cum)
+    fc.dkv_wait_epoch = ctx.last_bwd_epoch
+    C.attn_bwd_fused(attn_cuda._rows3(q), attn_cuda._rows3(dout), k, v, dq, items, qsegs, lse.contiguous(), delta,
+                     q.shape[0], float(scale), fc)
+    cuda_ext.note_launch()
+    # owner-side reduction of the inbox (waits for the peers' "gradients landed" epochs on the device)
+    tasks = reduce_tasks(plan, ctx, q.device)
+    dk = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
+    dv = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
+    inbox = ctx.inbox.tensor(0, (ctx.world * ctx.inbox_slot_stride,), torch.float32)
+    ctx.ticket_cum = (ctx.ticket_cum + 16 * int(tasks.shape[0])) & MASK32
+    C.reduce_dkv(inbox, ctx.inbox_slot_stride, ctx.inbox_kv_stride, dk, dv, tasks, fc, ctx.ticket_cum)
+    cuda_ext.note_launch()
+    ctx.last_bwd_epoch = ctx.epoch
+    return dq.to(q.dtype), dk, dv

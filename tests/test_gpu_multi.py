@@ -1,0 +1,126 @@
+"""Multi-GPU context parallelism on real GPUs: the fused NVLink path (default) and the torch.distributed
+fallback around the same kernels (RFA_B200_DISABLE_P2P=1), each against the dense fp32 oracle.
+Needs >= 2 GPUs; run with `-m gpu`."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+import ring_flash_attn_b200 as rfa
+from ring_flash_attn_b200.ops.dense import attention_oracle, varlen_attention_oracle
+from ring_flash_attn_b200.parallel import layouts
+from dist_utils import run_distributed
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _close(got, want, name, rel=5e-2, abs_=2e-2):
+    err = (got.float() - want.float()).abs().max().item()
+    lim = rel * want.float().abs().max().item() + abs_
+    assert err < lim, f"{name}: max err {err} > {lim}"
+
+
+def _batch_case(rank, world, scheme, causal, p2p, hq, hkv, s_local, iters):
+    os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    s = s_local * world
+    q = torch.randn(1, s, hq, 128, device=dev)
+    k = torch.randn(1, s, hkv, 128, device=dev)
+    v = torch.randn(1, s, hkv, 128, device=dev)
+    dout = torch.randn(1, s, hq, 128, device=dev)
+    for t in (q, k, v, dout):
+        dist.broadcast(t, src=0)
+    q, k, v, dout = (t.to(torch.bfloat16) for t in (q, k, v, dout))
+    rq, rk, rv = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref_out, ref_lse = attention_oracle(rq, rk, rv, causal)
+    ref_out.backward(dout.float())
+    shard = getattr(layouts, f"shard_{scheme}")
+    prefix = {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}[scheme]
+    fn = getattr(rfa, f"{prefix}_flash_attn_func")
+    for _ in range(iters):  # several calls exercise epoch / staging-parity reuse
+        lq, lk, lv = (shard(t, rank, world).detach().requires_grad_(True) for t in (q, k, v))
+        out, lse, _ = fn(lq, lk, lv, causal=causal, return_attn_probs=True)
+        out.backward(shard(dout, rank, world))
+        torch.cuda.synchronize()
+        _close(out, shard(ref_out, rank, world), "out")
+        _close(lse, shard(ref_lse, rank, world, dim=2), "lse", rel=2e-3, abs_=2e-3)
+        _close(lq.grad, shard(rq.grad, rank, world), "dq")
+        _close(lk.grad, shard(rk.grad, rank, world), "dk")
+        _close(lv.grad, shard(rv.grad, rank, world), "dv")
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("scheme,causal,hq,hkv,s_local", [
+    ("zigzag", True, 4, 4, 512), ("zigzag", True, 4, 2, 600), ("ring", True, 4, 2, 384), ("ring", False, 2, 2, 300),
+    ("stripe", True, 4, 1, 333),
+])
+def test_batch_schemes_2gpu(p2p, scheme, causal, hq, hkv, s_local):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_batch_case, 2, scheme, causal, p2p, hq, hkv, s_local, 3 if p2p else 1, backend="nccl")
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_zigzag_fused_more_gpus(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    run_distributed(_batch_case, world, "zigzag", True, True, 4, 2, 512, 2, backend="nccl")
+
+
+def _varlen_case(rank, world, which, p2p):
+    os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    unit = 2 * world
+    cu = [0, 30 * unit, 130 * unit, 200 * unit]
+    total = cu[-1]
+    hq, hkv = 4, 2
+    q = torch.randn(total, hq, 128, device=dev)
+    k = torch.randn(total, hkv, 128, device=dev)
+    v = torch.randn(total, hkv, 128, device=dev)
+    dout = torch.randn(total, hq, 128, device=dev)
+    for t in (q, k, v, dout):
+        dist.broadcast(t, src=0)
+    q, k, v, dout = (t.to(torch.bfloat16) for t in (q, k, v, dout))
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=dev)
+    rq, rk, rv = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref_out, ref_lse = varlen_attention_oracle(rq, rk, rv, cu_t.cpu(), True)
+    ref_out.backward(dout.float())
+    if which == "llama3":
+        sh = lambda t: layouts.shard_llama3(t, rank, world)  # noqa: E731
+    elif which == "ring":
+        sh = lambda t: layouts.shard_ring_varlen(t, cu, rank, world)  # noqa: E731
+    else:
+        sh = lambda t: layouts.shard_zigzag_varlen(t, cu, rank, world)  # noqa: E731
+    for _ in range(2):
+        lq, lk, lv = (sh(t).detach().requires_grad_(True) for t in (q, k, v))
+        if which == "llama3":
+            cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu_t, True, rank, world)
+            out, lse, _ = rfa.llama3_flash_attn_varlen_func(lq, lk, lv, cq, ck, mq, mk, heads_k_stride=1,
+                                                          local_k_slice=ks, causal=True, return_attn_probs=True)
+        else:
+            local_cu = cu_t // world
+            fn = rfa.ring_flash_attn_varlen_func if which == "ring" else rfa.zigzag_ring_flash_attn_varlen_func
+            out, lse, _ = fn(lq, lk, lv, local_cu, int((local_cu[1:] - local_cu[:-1]).max()), causal=True,
+                             return_attn_probs=True)
+        out.backward(sh(dout))
+        torch.cuda.synchronize()
+        _close(out, sh(ref_out), "out")
+        _close(lse, sh(ref_lse.transpose(0, 1)).transpose(0, 1), "lse", rel=2e-3, abs_=2e-3)
+        _close(lq.grad, sh(rq.grad), "dq")
+        _close(lk.grad, sh(rk.grad), "dk")
+        _close(lv.grad, sh(rv.grad), "dv")
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("which", ["ring", "zigzag", "llama3"])
+def test_varlen_schemes_2gpu(which, p2p):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_varlen_case, 2, which, p2p, backend="nccl")
