@@ -117,6 +117,7 @@ struct ReduceParams {
   uint32_t epoch;
   int world, my_rank;
 };
+constexpr int kReduceBlocksPerTask = 128;
 const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream);
 
 struct FwdParams {

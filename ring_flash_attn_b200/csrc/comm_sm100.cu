@@ -41,23 +41,41 @@ __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__
   __syncthreads();
   const long long n4 = static_cast<long long>(t.rows) * p.row_elems / 4;
   const long long off4 = static_cast<long long>(t.row0) * p.row_elems / 4;
+  const long long slot4 = p.slot_stride / 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int U = 4;
   for (int which = 0; which < 2; ++which) {
     const float4* in = reinterpret_cast<const float4*>(p.inbox + which * p.kv_stride) + off4;
     uint2* out = reinterpret_cast<uint2*>(which == 0 ? p.dk : p.dv) + off4;
-    const long long slot4 = p.slot_stride / 4;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+      float4 acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < p.world; ++r) {
-        if ((t.src_mask >> r) & 1u) {
-          const float4 v = __ldcv(in + r * slot4 + i);  // written by a peer: never serve it from a stale line
-          acc.x += v.x;
-          acc.y += v.y;
-          acc.z += v.z;
-          acc.w += v.w;
+        if (!((t.src_mask >> r) & 1u)) continue;
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          // written by a peer over NVLink: always read from L2, never from a stale L1 line
+          if (i < n4) v[u] = __ldcv(in + r * slot4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < n4) {
+            acc[u].x += v[u].x;
+            acc[u].y += v[u].y;
+            acc[u].z += v[u].z;
+            acc[u].w += v[u].w;
+          }
         }
       }
-      out[i] = pack4<T>(acc);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < n4) out[i] = pack4<T>(acc[u]);
+      }
     }
   }
   __syncthreads();
@@ -75,7 +93,7 @@ __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__
 
 const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream) {
   if (p.n_tasks <= 0) return nullptr;
-  dim3 grid(16, p.n_tasks, 1);
+  dim3 grid(kReduceBlocksPerTask, p.n_tasks, 1);
   if (dtype == kDtypeBF16) {
     comm::reduce_dkv_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
   } else {

@@ -122,9 +122,12 @@ def bwd_tables_fused(plan: CPPlan, row_offset: Dict[int, int], device, flag_of_s
                     qsegs.append([ch.row0, ch.rows, d, 0])
                     work += ch.rows - max(0, -d)
                 flag = flag_of_src.get(src, -1)
-                items.append((work, [row_offset[src] + t0, rows, begin, len(qsegs) - begin, flag, src, t0, 0]))
+                # launch order: local keys first, then sources in ring order (the order their K/V arrives),
+                # heaviest tiles first inside a source
+                step = (plan.rank - src) % plan.world
+                items.append(((step, -work), [row_offset[src] + t0, rows, begin, len(qsegs) - begin, flag, src, t0, 0]))
                 per_owner[src] += 1
-    items.sort(key=lambda t: -t[0])
+    items.sort(key=lambda t: t[0])
     c[key] = (_to_dev([it for _, it in items], 8, device), _to_dev(qsegs if qsegs else [[0, 0, 0, 0]], 4, device),
               per_owner)
     return c[key]

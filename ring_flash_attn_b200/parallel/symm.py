@@ -82,7 +82,7 @@ class PeerContext:
         self.stage_key = None
         self.inbox: Optional[PeerBuffer] = None
         self.inbox_key = None
-        self.n_push_ctas = int(os.environ.get("RFA_B200_PUSH_CTAS", "8"))
+        self.n_push_ctas = int(os.environ.get("RFA_B200_PUSH_CTAS", "24"))
 
     # -- buffers ------------------------------------------------------------------------------------
     def _quiesce(self):
@@ -312,7 +312,7 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     dk = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
     dv = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
     inbox = ctx.inbox.tensor(0, (ctx.world * ctx.inbox_slot_stride,), torch.float32)
-    ctx.ticket_cum = (ctx.ticket_cum + 16 * int(tasks.shape[0])) & MASK32
+    ctx.ticket_cum = (ctx.ticket_cum + 128 * int(tasks.shape[0])) & MASK32  # kReduceBlocksPerTask
     C.reduce_dkv(inbox, ctx.inbox_slot_stride, ctx.inbox_kv_stride, dk, dv, tasks, fc, ctx.ticket_cum)
     cuda_ext.note_launch()
     ctx.last_bwd_epoch = ctx.epoch
