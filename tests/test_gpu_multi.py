@@ -55,22 +55,36 @@ def _batch_case(rank, world, scheme, causal, p2p, hq, hkv, s_local, iters):
         _close(lv.grad, shard(rv.grad, rank, world), "dv")
 
 
+BATCH_CASES = [("zigzag", True, 4, 4, 512), ("zigzag", True, 4, 2, 600), ("ring", True, 4, 2, 384),
+               ("ring", False, 2, 2, 300), ("stripe", True, 4, 1, 333)]
+
+
+def _all_batch_cases(rank, world, p2p):
+    # one process group for every case: spawning + NCCL init dominates the test time otherwise
+    for scheme, causal, hq, hkv, s_local in BATCH_CASES:
+        _batch_case(rank, world, scheme, causal, p2p, hq, hkv, s_local, 3 if p2p else 1)
+
+
 @pytest.mark.parametrize("p2p", [True, False])
-@pytest.mark.parametrize("scheme,causal,hq,hkv,s_local", [
-    ("zigzag", True, 4, 4, 512), ("zigzag", True, 4, 2, 600), ("ring", True, 4, 2, 384), ("ring", False, 2, 2, 300),
-    ("stripe", True, 4, 1, 333),
-])
-def test_batch_schemes_2gpu(p2p, scheme, causal, hq, hkv, s_local):
+def test_batch_schemes_2gpu(p2p):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    run_distributed(_batch_case, 2, scheme, causal, p2p, hq, hkv, s_local, 3 if p2p else 1, backend="nccl")
+    run_distributed(_all_batch_cases, 2, p2p, backend="nccl")
+
+
+def _more_gpus(rank, world):
+    _batch_case(rank, world, "zigzag", True, True, 4, 2, 512, 2)
+    _batch_case(rank, world, "stripe", True, True, 4, 4, 300, 1)
+    _batch_case(rank, world, "ring", False, True, 2, 1, 256, 1)
+    for which in ("zigzag", "llama3"):
+        _varlen_case(rank, world, which, True)
 
 
 @pytest.mark.parametrize("world", [4, 8])
-def test_zigzag_fused_more_gpus(world):
+def test_fused_more_gpus(world):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    run_distributed(_batch_case, world, "zigzag", True, True, 4, 2, 512, 2, backend="nccl")
+    run_distributed(_more_gpus, world, backend="nccl")
 
 
 def _varlen_case(rank, world, which, p2p):
@@ -118,9 +132,13 @@ def _varlen_case(rank, world, which, p2p):
         _close(lv.grad, sh(rv.grad), "dv")
 
 
+def _all_varlen_cases(rank, world, p2p):
+    for which in ("ring", "zigzag", "llama3"):
+        _varlen_case(rank, world, which, p2p)
+
+
 @pytest.mark.parametrize("p2p", [True, False])
-@pytest.mark.parametrize("which", ["ring", "zigzag", "llama3"])
-def test_varlen_schemes_2gpu(which, p2p):
+def test_varlen_schemes_2gpu(p2p):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    run_distributed(_varlen_case, 2, which, p2p, backend="nccl")
+    run_distributed(_all_varlen_cases, 2, p2p, backend="nccl")
