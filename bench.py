@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Headline benchmark: zigzag ring flash attention, fwd+bwd iterations per second.
 
-Config (BASELINE.json "headline"): ``zigzag_ring_flash_attn_qkvpacked_func``, bf16, batch 1, 32 heads,
-head_dim 128, causal, 4096 tokens per GPU (sequence 32768 on 8 GPUs; weak scaling in tokens per GPU),
-synthetic random Q/K/V.  One step = forward + backward of the attention op through the public API.
+Config (BASELINE.json "headline"): ``zigzag_ring_flash_attn_qkvpacked_func``, bf16, batch 1, sequence 32768,
+32 heads, head_dim 128, causal, synthetic random Q/K/V.  The sequence is fixed and sharded over the N GPUs
+(strong scaling: 32768/N tokens per GPU, total attention work constant).  One step = forward + backward of
+the attention op through the public API.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--config readme]
 
@@ -155,9 +156,9 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     if args.config == "headline":
-        tokens, hq, hkv, api = 4096, 32, 32, "qkvpacked"
+        tokens, hq, hkv, api, scaling = 32768 // world, 32, 32, "qkvpacked", "strong"
     else:
-        tokens, hq, hkv, api = 8192, 32, 8, "kvpacked"
+        tokens, hq, hkv, api, scaling = 8192, 32, 8, "kvpacked", "weak"
     d = 128
     dtype = torch.bfloat16
 
@@ -215,12 +216,14 @@ def main():
             b.record()
             evs.append((a, b))
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        per = sorted(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([sum(per) / steps, per[len(per) // 2], per[0], per[-1]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stats.update(median=float(t[1]), min=float(t[2]), max=float(t[3]))
         return float(t[0])
 
+    stats = {}
     launches = None
     if args.impl == "ours":
         from ring_flash_attn_b200.ops import cuda_ext
@@ -229,14 +232,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    warm = max(args.warmup, 3)
-    # warm up once before counting launches
-    ms = None
+    # multi-GPU transports (NCCL channels, peer mappings) settle over the first several calls
+    warm = max(args.warmup, 3 if world == 1 else 8)
     for _ in range(warm):
         step(dev_in)
     if args.impl == "ours":
         counter.reset()
     ms = timed(lambda: step(dev_in), args.steps, 0)
+    step_stats = dict(stats)
     if args.impl == "ours":
         launches = counter.value
     e2e = None
@@ -256,7 +259,7 @@ def main():
         line = {
             "metric": f"zigzag_ring_flash_attn_{api}_func {args.mode} iter/s",
             "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms, "ms_per_step_stats": step_stats, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": (value / pub) if pub else None, "dtype": "bf16", "data": "synthetic",
             "impl": args.impl,
             "config": {"model": "attention op (Llama-style heads)", "global_batch": 1, "seq_len": S,

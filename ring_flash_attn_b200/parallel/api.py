@@ -57,6 +57,16 @@ class CPAttention(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None, None, None
 
 
+def _cp_apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic):
+    return CPAttention.apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic)
+
+
+try:  # torch.compile: treat the op as an opaque eager call (plans, peer memory and launches are host code)
+    _cp_apply = torch.compiler.disable(_cp_apply)
+except AttributeError:  # pragma: no cover - very old torch
+    pass
+
+
 def _check_common(q, dropout_p, window_size, alibi_slopes):
     if alibi_slopes is not None:
         raise NotImplementedError("alibi_slopes is not supported (same as the reference)")
@@ -126,7 +136,7 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
     b, s, hq, d = q.shape
     plan = _batch_plan(scheme, rank, world, b, s, bool(causal))
     plan.peer = lambda r, _a=(scheme, world, b, s, bool(causal)): _batch_plan(_a[0], r, *_a[1:])
-    out, lse = CPAttention.apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
+    out, lse = _cp_apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
                                  v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
                                  "ring", 1, deterministic)
     out = out.view(b, s, hq, d)
@@ -146,7 +156,7 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
     plan.peer = lambda r, _a=(scheme, world, cu_host, bool(causal)): _varlen_plan(_a[0], r, *_a[1:])
     if plan.q_rows != q.shape[0]:
         raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
-    out, lse = CPAttention.apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic)
+    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic)
     return (out, lse, None) if return_attn_probs else out
 
 
@@ -287,7 +297,7 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
     glob = _LLAMA3_GLOBAL.get((cu_q_host, cu_k_host, int(k_start), rank, world, bool(causal)))
     if glob is not None:
         plan.peer = lambda r, _g=glob, _w=world, _c=bool(causal), _t=q.shape[0]: _llama3_peer_plan(_g, _c, r, _w, _t)
-    out, lse = CPAttention.apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
+    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
                                  int(heads_k_stride), deterministic)
     return (out, lse, None) if return_attn_probs else out
 

@@ -79,9 +79,8 @@ class PeerContext:
         self.done_cum = 0
         self.ticket_cum = 0
         self.stage: Optional[PeerBuffer] = None
-        self.stage_key = None
+        self.stage_half = 0
         self.inbox: Optional[PeerBuffer] = None
-        self.inbox_key = None
         self.n_push_ctas = int(os.environ.get("RFA_B200_PUSH_CTAS", "24"))
 
     # -- buffers ------------------------------------------------------------------------------------
@@ -90,30 +89,30 @@ class PeerContext:
         dist.barrier(group=self.group)
 
     def ensure_stage(self, rows: int, hkv: int, dtype) -> None:
+        """Grow-only staging capacity (two call-parity halves).  The per-call layout is derived from the
+        current shapes, so batches of different length reuse the same mapping; a (collective) reallocation
+        only happens when a call needs more bytes than any call before it."""
         esize = torch.empty((), dtype=dtype).element_size()
-        key = (rows, hkv, esize)
-        if self.stage_key == key:
+        need_half = 2 * self.world * rows * hkv * 128 * esize  # [K|V][slot][rows] for one parity
+        if self.stage is not None and need_half <= self.stage_half:
             return
         self._quiesce()
         if self.stage is not None:
             self.stage.close()
-        row_bytes = hkv * 128 * esize
-        self.stage_half = 2 * self.world * rows * row_bytes  # one parity: [K|V][slot][rows]
+        self.stage_half = (need_half + 4095) // 4096 * 4096
         self.stage = PeerBuffer(2 * self.stage_half, self.device, self.group)
-        self.stage_key = key
         self._quiesce()
 
     def ensure_inbox(self, rows: int, hkv: int) -> None:
-        key = (rows, hkv)
-        if self.inbox_key == key:
+        need = self.world * 2 * rows * hkv * 128 * 4
+        self.inbox_kv_stride = rows * hkv * 128  # floats
+        self.inbox_slot_stride = 2 * self.inbox_kv_stride
+        if self.inbox is not None and need <= self.inbox.nbytes:
             return
         self._quiesce()
         if self.inbox is not None:
             self.inbox.close()
-        self.inbox_kv_stride = rows * hkv * 128  # floats
-        self.inbox_slot_stride = 2 * self.inbox_kv_stride
-        self.inbox = PeerBuffer(self.world * self.inbox_slot_stride * 4, self.device, self.group)
-        self.inbox_key = key
+        self.inbox = PeerBuffer(need, self.device, self.group)
         self._quiesce()
 
     # -- per-call context object --------------------------------------------------------------------
