@@ -83,7 +83,6 @@ def main():
     torch.cuda.set_device(rank % torch.cuda.device_count())
     dist.init_process_group("nccl", device_id=torch.device("cuda", rank % torch.cuda.device_count()))
     world = dist.get_world_size()
-    LOCAL_GROUP = dist.new_group([rank]) if world > 1 else None
     groups = [dist.new_group([r]) for r in range(world)] if world > 1 else []
     if world > 1:
         LOCAL_GROUP = groups[rank]

@@ -14,9 +14,10 @@
 //   dK  += dS^T Q_i        (A = dS^T smem K-major, B = Q MN-major)
 //   dQ_i^T = K^T dS_i      (A = K MN-major, B = dS^T MN-major)  -> fp32 smem -> TMA reduce-add
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 softmax (thread == key row), warps 8-11 dQ drain (thread == head-dim lane).
-// TMEM (512 columns): S^T x2 [0,128)  dP^T [128,192)  dQ^T [192,256)  dV [256,384)  dK [384,512).
+// Warp roles (512 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 lse/delta
+// prefetch, warps 4-7 and 8-11 softmax (thread == key row; each warpgroup owns 32 of the 64 query columns, so
+// two warps per scheduler hide each other's latencies), warps 12-15 dQ drain (thread == head-dim lane).
+// TMEM (512 columns): S^T x2 [0,128) (P^T halves parked at +0 and +32 of a buffer)  dP^T [128,192)  dQ^T [192,256)  dV [256,384)  dK [384,512).
 #include <math_constants.h>
 #include <stdio.h>
 
@@ -31,7 +32,7 @@ constexpr int kD = 128;
 constexpr int kTileK = 128;  // keys per CTA
 constexpr int kTileQ = 64;   // queries per inner iteration
 constexpr int kStages = 3;   // Q/dO ring
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kKVBytes = kTileK * kD * 2;          // 32 KB each for K and V
 constexpr int kQBytes = kTileQ * kD * 2;           // 16 KB each for Q and dO
 constexpr int kQHalf = kQBytes / 2;                // 64-wide swizzled sub-tile of a 64-row tile (8 KB)
@@ -47,7 +48,8 @@ struct Barriers {
   uint64_t qdo_empty[kStages];
   uint64_t stat_full[kStages];
   uint64_t s_full[2];
-  uint64_t p_ready;
+  uint64_t p_ready[2];  // one per S^T buffer: with S^T look-ahead a fast warp may reach tile i+1 before a slow
+                        // warp has arrived for tile i, and must not be counted in tile i's phase
   uint64_t dp_full;
   uint64_t ds_ready;
   uint64_t dq_full;
@@ -124,9 +126,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     mbar_init(&bars->s_full[0], 1);
     mbar_init(&bars->s_full[1], 1);
-    mbar_init(&bars->p_ready, 128);
+    mbar_init(&bars->p_ready[0], 256);
+    mbar_init(&bars->p_ready[1], 256);
     mbar_init(&bars->dp_full, 1);
-    mbar_init(&bars->ds_ready, 128);
+    mbar_init(&bars->ds_ready, 256);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_free, 128);
     mbar_init(&bars->dkv_done, 1);
@@ -147,7 +150,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int total_tiles = tiles_per_head * group;
 
   if (warp < 4) {
-    reg_dealloc<72>();
+    reg_dealloc<72>();  // 128*72 + 384*144 = 512*126 <= 512*128
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
@@ -188,7 +191,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
-      if (lane == 0 && total_tiles > 0) {
+      // Warp-uniform loop (descriptors live in uniform registers); one elected lane issues and commits.
+      if (total_tiles > 0) {
+        const bool leader = elect_one();
         constexpr uint32_t fmt = Pack2<T>::kFmt;
         constexpr uint32_t idesc_st = umma_idesc_f16(fmt, kTileK, kTileQ, 0, 0);  // S^T, dP^T
         constexpr uint32_t idesc_dv = umma_idesc_f16(fmt, kTileK, kD, 0, 1);      // dV (A tmem), dK (A smem)
@@ -196,36 +201,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t k_base = smem_u32(smem_k), v_base = smem_u32(smem_v);
         const uint32_t qdo_base = smem_u32(smem_qdo), ds_base = smem_u32(smem_ds);
 
+        // Descriptors as (lo, hi) halves: hi is a constant, lo = (base >> 4) + compile-time k step.
+        constexpr uint32_t hi = umma_desc_hi(1024, kSwizzle128B);
+        const uint32_t k_km = umma_desc_lo(k_base, 16);        // K tile, K-major A (S^T)
+        const uint32_t v_km = umma_desc_lo(v_base, 16);        // V tile, K-major A (dP^T)
+        const uint32_t k_mn = umma_desc_lo(k_base, kKVHalf);   // K tile, MN-major A (dQ^T)
+        const uint32_t ds_km = umma_desc_lo(ds_base, 16);      // dS^T, K-major A (dK) / MN-major B (dQ^T)
+        const uint32_t q_km0 = umma_desc_lo(qdo_base, 16);     // stage 0 Q, K-major B
+        const uint32_t q_mn0 = umma_desc_lo(qdo_base, kQHalf); // stage 0 Q, MN-major B
+        constexpr uint32_t stage_step = (2 * kQBytes) >> 4, do_step = kQBytes >> 4;
+
         // S^T / dP^T: A = K or V tile (128 rows, K-major), B = Q or dO tile (64 rows, K-major)
-        auto issue_kq = [&](uint32_t d_col, uint32_t a_base, uint32_t b_base) {
+        auto issue_kq = [&](uint32_t d_col, uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
           for (int k = 0; k < kD / 16; ++k) {
-            const uint32_t a = a_base + (k >> 2) * kKVHalf + (k & 3) * 32;
-            const uint32_t b = b_base + (k >> 2) * kQHalf + (k & 3) * 32;
-            umma_ss(d_col, umma_smem_desc(a, 16, 1024, kSwizzle128B), umma_smem_desc(b, 16, 1024, kSwizzle128B),
-                    idesc_st, k > 0);
+            const uint32_t oa = ((k >> 2) * kKVHalf + (k & 3) * 32) >> 4;
+            const uint32_t ob = ((k >> 2) * kQHalf + (k & 3) * 32) >> 4;
+            umma_ss2(d_col, a_lo + oa, hi, b_lo + ob, hi, idesc_st, k > 0);
           }
-        };
-        // B = [64 rows][128 dims] tile read MN-major (N = dims): LBO = 8 KB between the two 64-dim halves,
-        // SBO = 1 KB between 8-row groups, 16 rows (2 KB) per MMA.
-        auto qdo_mn_desc = [&](uint32_t base, int k) {
-          return umma_smem_desc(base + k * 2048, kQHalf, 1024, kSwizzle128B);
         };
 
         mbar_wait(&bars->kv_full, 0);
         tc_fence_after();
 
         uint32_t slot = 0, phase = 0;
-        uint32_t ph_p = 0, ph_ds = 0, ph_dqfree = 0;
+        uint32_t ph_p[2] = {0, 0};
+        uint32_t ph_ds = 0, ph_dqfree = 0;
         // software pipeline: S^T of tile i+1 is issued before the dV/dK/dQ GEMMs of tile i
         int issued_s = 0;          // tiles whose S^T has been issued
         uint32_t s_slot = 0, s_phase = 0;  // ring position used by the next S^T issue
         auto issue_s = [&]() {
           mbar_wait(&bars->qdo_full[s_slot], s_phase);
           tc_fence_after();
-          const uint32_t qb = qdo_base + s_slot * 2 * kQBytes;
-          issue_kq(tmem + kColS + (issued_s & 1) * 64, k_base, qb);
-          umma_commit(&bars->s_full[issued_s & 1]);
+          if (leader) {
+            issue_kq(tmem + kColS + (issued_s & 1) * 64, k_km, q_km0 + s_slot * stage_step);
+            umma_commit(&bars->s_full[issued_s & 1]);
+          }
           ++issued_s;
           if (++s_slot == kStages) {
             s_slot = 0;
@@ -234,39 +245,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         };
         issue_s();
         // dP^T of tile 0
-        issue_kq(tmem + kColDP, v_base, qdo_base + kQBytes);
-        umma_commit(&bars->dp_full);
+        if (leader) {
+          issue_kq(tmem + kColDP, v_km, q_km0 + do_step);
+          umma_commit(&bars->dp_full);
+        }
         for (int i = 0; i < total_tiles; ++i) {
-          const uint32_t qb = qdo_base + slot * 2 * kQBytes;
-          const uint32_t dob = qb + kQBytes;
-          if (i + 1 < total_tiles) issue_s();
+          const uint32_t q_mn = q_mn0 + slot * stage_step;  // Q_i read MN-major (B of dK)
+          const uint32_t do_mn = q_mn + do_step;            // dO_i read MN-major (B of dV)
+          if (i + 1 < total_tiles && !(p.debug & 2)) issue_s();
           // dV += P^T dO   (P^T: bf16 in the first 32 columns of this tile's S^T buffer)
-          mbar_wait(&bars->p_ready, ph_p);
-          ph_p ^= 1;
+          mbar_wait(&bars->p_ready[i & 1], ph_p[i & 1]);
+          ph_p[i & 1] ^= 1;
           tc_fence_after();
+          if (leader)
 #pragma unroll
           for (int k = 0; k < kTileQ / 16; ++k)
-            umma_ts(tmem + kColDV, tmem + kColS + (i & 1) * 64 + k * 8, qdo_mn_desc(dob, k), idesc_dv,
-                    (i > 0 || k > 0) ? 1u : 0u);
+            umma_ts2(tmem + kColDV, tmem + kColS + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8, do_mn + k * (2048 >> 4), hi, idesc_dv,
+                     (i > 0 || k > 0) ? 1u : 0u);
           // dK += dS^T Q ; dQ^T = K^T dS
           mbar_wait(&bars->ds_ready, ph_ds);
           ph_ds ^= 1;
           tc_fence_after();
+          if (leader)
 #pragma unroll
           for (int k = 0; k < kTileQ / 16; ++k)
-            umma_ss(tmem + kColDK, umma_smem_desc(ds_base + k * 32, 16, 1024, kSwizzle128B), qdo_mn_desc(qb, k),
-                    idesc_dv, (i > 0 || k > 0) ? 1u : 0u);
+            umma_ss2(tmem + kColDK, ds_km + k * (32 >> 4), hi, q_mn + k * (2048 >> 4), hi, idesc_dv,
+                     (i > 0 || k > 0) ? 1u : 0u);
           if (i > 0) {  // previous dQ^T must have been drained out of TMEM
             mbar_wait(&bars->dq_free, ph_dqfree);
             ph_dqfree ^= 1;
             tc_fence_after();
           }
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kTileK / 16; ++k)
-            umma_ss(tmem + kColDQ, umma_smem_desc(k_base + k * 2048, kKVHalf, 1024, kSwizzle128B),
-                    umma_smem_desc(ds_base + k * 2048, 16, 1024, kSwizzle128B), idesc_dq, k > 0);
-          umma_commit(&bars->dq_full);
-          umma_commit(&bars->qdo_empty[slot]);  // Q_i / dO_i no longer needed once everything above retires
+            for (int k = 0; k < kTileK / 16; ++k)
+              umma_ss2(tmem + kColDQ, k_mn + k * (2048 >> 4), hi, ds_km + k * (2048 >> 4), hi, idesc_dq, k > 0);
+            umma_commit(&bars->dq_full);
+            umma_commit(&bars->qdo_empty[slot]);  // Q_i / dO_i no longer needed once everything above retires
+          }
           if (++slot == kStages) {
             slot = 0;
             phase ^= 1;
@@ -276,11 +292,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (i + 1 < total_tiles) {
             mbar_wait(&bars->qdo_full[slot], phase);  // already landed (S^T of that tile was issued)
             tc_fence_after();
-            issue_kq(tmem + kColDP, v_base, qdo_base + slot * 2 * kQBytes + kQBytes);
-            umma_commit(&bars->dp_full);
+            if (leader) {
+              issue_kq(tmem + kColDP, v_km, q_km0 + slot * stage_step + do_step);
+              umma_commit(&bars->dp_full);
+            }
           }
+          if (i + 1 < total_tiles && (p.debug & 2)) issue_s();
+          __syncwarp();
         }
-        umma_commit(&bars->dkv_done);
+        if (leader) umma_commit(&bars->dkv_done);
+        __syncwarp();
       }
     } else if (warp == 3) {
       // ---------------------------------------------------------------- per-query statistics producer
@@ -323,10 +344,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ softmax warpgroup (thread == key row)
-    reg_alloc<216>();
-    const int wg_tid = threadIdx.x - 128;
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ softmax warpgroups (thread == key row)
+    reg_alloc<144>();
+    const int half = (warp - 4) >> 2;             // which 32 query columns of every tile this warpgroup owns
+    const int c0 = half * 32;
+    const int wg_tid = (threadIdx.x - 128) & 127;
     const int key = wg_tid;                       // row in the key tile
     const bool key_ok = key < it.kv_rows;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -338,11 +361,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int si = 0; si < it.seg_count; ++si) {
         const QGeom g = q_geom(p.qsegs[it.seg_begin + si]);
         for (int ti = g.t_begin; ti < g.t_end; ++ti, ++i) {
-          const float* st = smem_stat + st_slot * 2 * kTileQ;
+          const float* st = smem_stat + st_slot * 2 * kTileQ + c0;
           mbar_wait(&bars->stat_full[st_slot], st_phase);
           if (++st_slot == kStages) {
             st_slot = 0;
             st_phase ^= 1;
+          }
+          float lse2[32];
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(st + c);
+            lse2[c] = v4.x; lse2[c + 1] = v4.y; lse2[c + 2] = v4.z; lse2[c + 3] = v4.w;
+          }
+          if (p.debug & 1) {
+            const int head = kv_head * group + gq;
+            for (int c = 0; c < 32; ++c) {
+              const int qi = ti * kTileQ + c0 + c;
+              float v = CUDART_INF_F;
+              if (qi < g.q_len) {
+                const int row = g.q_row0 + qi;
+                const size_t b = row / p.lse_S, sidx = row % p.lse_S;
+                const float x = p.lse[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx];
+                v = x == -CUDART_INF_F ? CUDART_INF_F : x * 1.4426950408889634f;
+              }
+              lse2[c] = v;
+            }
           }
 
           const int buf = i & 1;
@@ -350,51 +393,70 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&bars->s_full[buf], ph_s[buf]);
           ph_s[buf] ^= 1;
           tc_fence_after();
-          uint32_t sr[64];
-          tmem_ld32(t_s, sr);
-          tmem_ld32(t_s + 32, sr + 32);
+          uint32_t sr[32];
+          tmem_ld32(t_s + c0, sr);
           tmem_ld_wait();
           // causal boundary: key visible to query qi iff key <= qi + diag  <=>  qi >= key - diag
           const long long first_q = static_cast<long long>(key) - g.diag - static_cast<long long>(ti) * kTileQ;
           const int q_lo = !key_ok ? kTileQ : (first_q < 0 ? 0 : (first_q > kTileQ ? kTileQ : static_cast<int>(first_q)));
-          float pr[64];
+          float pr[32];
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float e = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -st[c]));
-            pr[c] = c >= q_lo ? e : 0.f;
+          for (int c = 0; c < 32; ++c) {
+            const float e = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -lse2[c]));
+            pr[c] = (c0 + c) >= q_lo ? e : 0.f;
           }
           {
-            uint32_t pk[32];
+            uint32_t pk[16];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) pk[c] = Pack2<T>::pack(pr[2 * c], pr[2 * c + 1]);
-            tmem_st32(t_s, pk);
+            for (int c = 0; c < 16; ++c) pk[c] = Pack2<T>::pack(pr[2 * c], pr[2 * c + 1]);
+            // each warpgroup parks its half of P^T inside the S^T columns it has already consumed itself
+            // (half 0 -> columns [0,16), half 1 -> [32,48)); writing into the other group's columns would race
+            tmem_st16(t_s + c0, pk);
           }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&bars->p_ready);
+          mbar_arrive(&bars->p_ready[buf]);
 
           // dS^T = P^T o (dP^T - delta) * scale  -> shared memory, 128-byte swizzled rows of 64 bf16
+          float dlt[32];
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(st + kTileQ + c);
+            dlt[c] = v4.x; dlt[c + 1] = v4.y; dlt[c + 2] = v4.z; dlt[c + 3] = v4.w;
+          }
+          if (p.debug & 1) {
+            const int head = kv_head * group + gq;
+            for (int c = 0; c < 32; ++c) {
+              const int qi = ti * kTileQ + c0 + c;
+              float v = 0.f;
+              if (qi < g.q_len) {
+                const int row = g.q_row0 + qi;
+                const size_t b = row / p.lse_S, sidx = row % p.lse_S;
+                v = p.delta[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx];
+              }
+              dlt[c] = v;
+            }
+          }
           mbar_wait(&bars->dp_full, ph_dp);
           ph_dp ^= 1;
           tc_fence_after();
-          uint32_t dpr[64];
-          tmem_ld32(tmem + kColDP + lane_addr, dpr);
-          tmem_ld32(tmem + kColDP + lane_addr + 32, dpr + 32);
+          uint32_t dpr[32];
+          tmem_ld32(tmem + kColDP + lane_addr + c0, dpr);
           tmem_ld_wait();
           uint8_t* ds_row = smem_ds + key * 128;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int ch = 0; ch < 4; ++ch) {
             uint4 v;
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = ch * 8 + e * 2;
-              const float d0 = pr[c] * (__uint_as_float(dpr[c]) - st[kTileQ + c]) * p.scale;
-              const float d1 = pr[c + 1] * (__uint_as_float(dpr[c + 1]) - st[kTileQ + c + 1]) * p.scale;
+              const float d0 = pr[c] * (__uint_as_float(dpr[c]) - dlt[c]) * p.scale;
+              const float d1 = pr[c + 1] * (__uint_as_float(dpr[c + 1]) - dlt[c + 1]) * p.scale;
               w[e] = Pack2<T>::pack(d0, d1);
             }
             v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
-            *reinterpret_cast<uint4*>(ds_row + ((ch ^ (key & 7)) << 4)) = v;
+            *reinterpret_cast<uint4*>(ds_row + (((half * 4 + ch) ^ (key & 7)) << 4)) = v;
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -402,20 +464,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-    // ---------------------------------------------------------------- epilogue: dK / dV tile -> global (fp32)
+    // ---------------------------------------------------------------- epilogue: dK (half 0) / dV (half 1) -> global
     const bool remote = p.dkv.world > 0;
     const int row = (remote ? it.out_row0 : it.kv_row0) + key;
     if (remote && wg_tid == 0) {
       // the owner must have drained what we stored into its inbox during the previous backward call
       wait_epoch(p.dkv.my_pad + kPadInboxFree + it.owner, p.dkv.wait_epoch, "inbox reuse");
     }
-    if (remote) named_bar_sync(1, 128);
+    if (remote) named_bar_sync(1 + half, 128);
     if (total_tiles > 0) {
       mbar_wait(&bars->dkv_done, 0);
       tc_fence_after();
     }
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = half;
       float* base = remote ? (which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner])
                            : (which == 0 ? p.dk : p.dv);
       float* dst = base + (static_cast<size_t>(row) * p.hkv + kv_head) * kD;
@@ -440,8 +502,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (remote) {
       // publish: the last tile destined for an owner raises that owner's "gradients landed" flag
       __threadfence_system();
-      named_bar_sync(1, 128);
-      if (wg_tid == 0) {
+      named_bar_sync(3, 256);  // both halves (dK and dV) have been stored and fenced
+      if (half == 0 && wg_tid == 0) {
         const uint32_t old = atomicAdd(p.dkv.sent_count + it.owner, 1u);
         if (old + 1u == p.dkv.sent_target[it.owner]) {
           __threadfence_system();
@@ -451,8 +513,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ dQ drain warpgroup (thread == dim)
-    reg_alloc<216>();
-    const int wg_tid = threadIdx.x - 256;
+    reg_alloc<144>();
+    const int wg_tid = threadIdx.x - 384;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     uint32_t ph = 0;
     int i = 0;
@@ -472,11 +534,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_arrive(&bars->dq_free);
           // the previous tile's reduce must have finished reading the staging buffer
           if (wg_tid == 0) tma_store_wait_read<0>();
-          named_bar_sync(2, 128);
+          named_bar_sync(4, 128);
 #pragma unroll
           for (int q = 0; q < kTileQ; ++q) smem_dq[q * kD + wg_tid] = __uint_as_float(r[q]);
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          named_bar_sync(4, 128);
           if (wg_tid == 0) {
             tma_reduce_add_3d(&tm_dq, smem_dq, 0, head, g.q_row0 + ti * kTileQ);
             tma_store_commit();

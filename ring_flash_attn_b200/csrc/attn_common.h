@@ -131,6 +131,7 @@ struct FwdParams {
   float scale_log2;  // scale * log2(e)
   const uint32_t* ready_flags;  // fused mode only: this rank's signal pad (kPadKvReady + src)
   uint32_t ready_epoch;
+  unsigned long long* trace;  // RFA_TRACE builds only: per-iteration clock64 stamps of CTA 0 (else unused)
   int n_items;       // compute CTAs = n_items * hq, laid out after the push CTAs
   PushParams push;   // n_ctas == 0 when there is nothing to push
   SignalParams sig;
@@ -168,6 +169,7 @@ struct BwdParams {
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
   int n_items;
+  int debug;  // bisecting aid: bit0 = stats straight from global, bit1 = no S^T look-ahead
   PushParams push;
   SignalParams sig;
   DkvParams dkv;
@@ -180,6 +182,8 @@ struct ProbeConfig {
   int kdim;  // 128 or 64
   int lbo_a, sbo_a, kstep_a;
   int lbo_b, sbo_b, kstep_b;
+  int reps;                 // > 1: repeat the k-loop to measure MMA throughput
+  unsigned long long* cycles;  // optional: elapsed SM cycles of the issue-to-completion window
 };
 
 // dtype codes shared with the Python side

@@ -27,6 +27,18 @@ namespace rfa {
 
 namespace fwd {
 
+#ifdef RFA_TRACE
+// slot layout per key-tile iteration (16 stamps): 0-5 MMA thread, 6-10 softmax tile 0, 11-15 softmax tile 1
+#define RFA_STAMP(cond, iter, slot)                                                              \
+  do {                                                                                            \
+    if ((cond) && cta == 0 && p.trace != nullptr && (iter) < 64) p.trace[(iter)*16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define RFA_STAMP(cond, iter, slot) \
+  do {                              \
+  } while (0)
+#endif
+
 constexpr int kD = 128;             // head dim
 constexpr int kTile = 128;          // rows per MMA tile (queries and keys)
 constexpr int kStages = 4;          // K/V ring slots
@@ -134,7 +146,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   if (warp < 4) {
-   reg_dealloc<72>();
+   reg_dealloc<88>();
    if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -174,7 +186,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the loop (so addresses / descriptors stay in uniform registers); one elected lane
+    // issues the tcgen05 instructions and commits.
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_qk = umma_idesc_f16(Pack2<T>::kFmt, kTile, kTile, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(Pack2<T>::kFmt, kTile, kD, 0, 1);
       const uint32_t q_base = smem_u32(smem_q);
@@ -182,26 +197,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t col_s[2] = {tmem + kColS0, tmem + kColS1};
       const uint32_t col_o[2] = {tmem + kColO0, tmem + kColO1};
 
+      // Descriptors: high words are constants, low words are (base >> 4) + a compile-time step per k.
+      constexpr uint32_t hi = umma_desc_hi(1024, kSwizzle128B);
+      const uint32_t q_lo[2] = {umma_desc_lo(q_base, 16), umma_desc_lo(q_base + kTileBytes, 16)};
+      const uint32_t k_lo0 = umma_desc_lo(kv_base, 16);           // K tile read K-major
+      const uint32_t v_lo0 = umma_desc_lo(kv_base, kHalfBytes);   // V tile read MN-major (LBO = 64-dim half)
+      constexpr uint32_t slot_step = kTileBytes >> 4;
+
       auto issue_qk = [&](int t, uint32_t k_slot) {
-        const uint32_t qa = q_base + t * kTileBytes;
-        const uint32_t kb = kv_base + k_slot * kTileBytes;
+        const uint32_t a0 = q_lo[t], b0 = k_lo0 + k_slot * slot_step;
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) {
-          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-          umma_ss(col_s[t], umma_smem_desc(qa + off, 16, 1024, kSwizzle128B),
-                  umma_smem_desc(kb + off, 16, 1024, kSwizzle128B), idesc_qk, k > 0);
+          const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
+          umma_ss2(col_s[t], a0 + off, hi, b0 + off, hi, idesc_qk, k > 0);
         }
         umma_commit(&bars->s_full[t]);
       };
       auto issue_pv = [&](int t, uint32_t v_slot, bool accumulate) {
-        const uint32_t vb = kv_base + v_slot * kTileBytes;
+        // V tile is [128 keys][2 x 64 dims] -> MN-major B: LBO = stride between the two 64-wide halves,
+        // SBO = stride between 8-key groups; one MMA consumes 16 keys = 2048 bytes.
+        const uint32_t b0 = v_lo0 + v_slot * slot_step;
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          // V tile is [128 keys][2 x 64 dims] -> MN-major B: LBO = stride between the two 64-wide halves,
-          // SBO = stride between 8-key groups; one MMA consumes 16 keys = 2048 bytes.
-          umma_ts(col_o[t], col_s[t] + k * 8, umma_smem_desc(vb + k * 2048, kHalfBytes, 1024, kSwizzle128B),
-                  idesc_pv, (accumulate || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < kTile / 16; ++k)
+          umma_ts2(col_o[t], col_s[t] + k * 8, b0 + k * (2048 >> 4), hi, idesc_pv, (accumulate || k > 0) ? 1u : 0u);
       };
 
       mbar_wait(&bars->q_full[0], 0);
@@ -219,59 +237,76 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           phase ^= 1;
         }
       };
+      int xi = 0;
       for (int si = 0; si < it.seg_count; ++si) {
         const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
-        for (int jj = 0; jj < g.n_tiles; ++jj) {
+        for (int jj = 0; jj < g.n_tiles; ++jj, ++xi) {
           const bool a0 = tile_active(g, it, 0, jj);
           const bool a1 = tile_active(g, it, 1, jj);
           const uint32_t k_slot = slot, k_phase = phase;
           advance();
           const uint32_t v_slot = slot, v_phase = phase;
           advance();
+          RFA_STAMP(true, xi, 0);
           mbar_wait(&bars->kv_full[k_slot], k_phase);
           tc_fence_after();
-          if (a0) issue_qk(0, k_slot);
+          RFA_STAMP(true, xi, 1);
+          if (a0 && leader) issue_qk(0, k_slot);
           if (pend1) {  // PV_1 of the previous key tile (its V slot is still resident)
             mbar_wait(&bars->p_ready[1], p_phase[1]);
             p_phase[1] ^= 1;
             tc_fence_after();
-            issue_pv(1, pend1_slot, o_started[1]);
+            RFA_STAMP(true, xi, 2);
+            if (leader) {
+              issue_pv(1, pend1_slot, o_started[1]);
+              umma_commit(&bars->kv_empty[pend1_slot]);
+            }
             o_started[1] = true;
-            umma_commit(&bars->kv_empty[pend1_slot]);
             pend1 = false;
           }
-          if (a1) issue_qk(1, k_slot);
-          umma_commit(&bars->kv_empty[k_slot]);
+          if (leader) {
+            if (a1) issue_qk(1, k_slot);
+            umma_commit(&bars->kv_empty[k_slot]);
+          }
+          RFA_STAMP(true, xi, 3);
           mbar_wait(&bars->kv_full[v_slot], v_phase);
           tc_fence_after();
           if (a0) {
             mbar_wait(&bars->p_ready[0], p_phase[0]);
             p_phase[0] ^= 1;
             tc_fence_after();
-            issue_pv(0, v_slot, o_started[0]);
+            RFA_STAMP(true, xi, 4);
+            if (leader) issue_pv(0, v_slot, o_started[0]);
+            RFA_STAMP(true, xi, 5);
             o_started[0] = true;
           }
           if (a1) {
             pend1 = true;
             pend1_slot = v_slot;
-          } else {
+          } else if (leader) {
             umma_commit(&bars->kv_empty[v_slot]);
           }
+          __syncwarp();
         }
       }
       if (pend1) {
         mbar_wait(&bars->p_ready[1], p_phase[1]);
         tc_fence_after();
-        issue_pv(1, pend1_slot, o_started[1]);
-        umma_commit(&bars->kv_empty[pend1_slot]);
+        if (leader) {
+          issue_pv(1, pend1_slot, o_started[1]);
+          umma_commit(&bars->kv_empty[pend1_slot]);
+        }
       }
-      umma_commit(&bars->o_done[0]);
-      umma_commit(&bars->o_done[1]);
+      if (leader) {
+        umma_commit(&bars->o_done[0]);
+        umma_commit(&bars->o_done[1]);
+      }
+      __syncwarp();
     }
    }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
-    reg_alloc<216>();
+    reg_alloc<208>();
     const int t = (warp - 4) >> 2;                 // tile handled by this warpgroup
     const int row_in_tile = ((warp & 3) << 5) | lane;
     const int n_rows = t == 0 ? n_rows0 : n_rows1;
@@ -285,14 +320,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     bool first = true;
     uint32_t s_phase = 0;
 
+    // The two softmax warpgroups take turns in the MUFU-heavy exp section (named barriers 1 + t).  Without
+    // the hand-off both tiles drift into phase: their exp sections then share the 4 SFU lanes per scheduler,
+    // and the tensor pipe idles while both run.  Strict alternation keeps one tile's softmax under the other
+    // tile's MMAs.  Both groups execute one hand-off per key tile, active or not, so the counts always match.
+    int handoffs_left = 0;
+    if (has_t1) {
+      for (int si = 0; si < it.seg_count; ++si) handoffs_left += seg_geom(p.segs[it.seg_begin + si], it).n_tiles;
+      if (t == 1 && handoffs_left > 0) named_bar_arrive(1, 256);  // tile 0 goes first
+    }
+    auto turn_wait = [&]() {
+      if (has_t1) named_bar_sync(1 + t, 256);
+    };
+    auto turn_pass = [&]() {
+      if (has_t1) {
+        --handoffs_left;
+        if (!(t == 1 && handoffs_left == 0)) named_bar_arrive(1 + (1 - t), 256);  // nobody waits after the last one
+      }
+    };
+
     if (n_rows > 0) {
+      int xi = 0;
+      const bool stamper = (threadIdx.x & 127) == 0;
       for (int si = 0; si < it.seg_count; ++si) {
         const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
-        for (int jj = 0; jj < g.n_tiles; ++jj) {
-          if (!tile_active(g, it, t, jj)) continue;
+        for (int jj = 0; jj < g.n_tiles; ++jj, ++xi) {
+          if (!tile_active(g, it, t, jj)) {
+            turn_wait();
+            turn_pass();
+            continue;
+          }
           mbar_wait(&bars->s_full[t], s_phase);
           s_phase ^= 1;
           tc_fence_after();
+          RFA_STAMP(stamper, xi, 6 + 5 * t);
 
           uint32_t sr[128];
           tmem_ld32(t_s + 0, sr + 0);
@@ -300,6 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld32(t_s + 64, sr + 64);
           tmem_ld32(t_s + 96, sr + 96);
           tmem_ld_wait();
+          RFA_STAMP(stamper, xi, 7 + 5 * t);
           float s[128];
 #pragma unroll
           for (int c = 0; c < 128; ++c) s[c] = __uint_as_float(sr[c]);
@@ -346,6 +408,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           first = false;
           const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * p.scale_log2;
           float l0 = 0.f, l1 = 0.f;
+          turn_wait();
+          RFA_STAMP(stamper, xi, 8 + 5 * t);
 #pragma unroll
           for (int c = 0; c < 128; c += 32) {
             uint32_t pk[16];
@@ -359,10 +423,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             tmem_st16(t_s + (c >> 1), pk);
           }
+          turn_pass();
+          RFA_STAMP(stamper, xi, 9 + 5 * t);
           l += l0 + l1;
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars->p_ready[t]);
+          RFA_STAMP(stamper, xi, 10 + 5 * t);
         }
       }
 

@@ -3,6 +3,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
+
 #include "attn_common.h"
 #include "peer_mem.h"
 
@@ -25,6 +27,8 @@ TensorView view3(const at::Tensor& t, const char* name) {
 }
 
 void check(const char* err) { TORCH_CHECK(err == nullptr, "ring_flash_attn_b200 kernel launch failed: ", err); }
+
+extern at::Tensor g_trace;
 
 // Fused-mode context shared by the forward and backward launches (all lists are indexed by rank).
 struct FusedCtx {
@@ -91,6 +95,7 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   p.scale = static_cast<float>(scale);
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
   p.n_items = static_cast<int>(items.size(0));
+  p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
@@ -103,6 +108,10 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
                                view3(v, "v"), p, at::cuda::getCurrentCUDAStream()));
   }
 }
+
+at::Tensor g_trace;  // optional clock64 trace buffer (RFA_TRACE builds)
+
+void set_trace(const c10::optional<at::Tensor>& t) { g_trace = t.has_value() ? *t : at::Tensor(); }
 
 void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
               const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale) {
@@ -152,6 +161,7 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
   TensorView dqv{dq_accum.data_ptr(), dq_accum.size(0), static_cast<int>(dq_accum.size(1)), dq_accum.stride(0),
                  dq_accum.stride(1)};
   p.n_items = static_cast<int>(items.size(0));
+  if (const char* e = std::getenv("RFA_B200_DEBUG")) p.debug = std::atoi(e);
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
@@ -218,11 +228,13 @@ void reduce_dkv(const at::Tensor& inbox, int64_t slot_stride, int64_t kv_stride,
 at::Tensor probe(const at::Tensor& a, const at::Tensor& b, std::vector<int64_t> cfg) {
   // a: (rows, 128) or (128, kdim) bf16 ; b likewise; cfg = {a_kind, b_kind, n, kdim, lbo_a, sbo_a, kstep_a, lbo_b, sbo_b, kstep_b}
   const c10::cuda::CUDAGuard guard(a.device());
-  TORCH_CHECK(cfg.size() == 10);
+  TORCH_CHECK(cfg.size() == 10 || cfg.size() == 11);
   rfa::ProbeConfig c{static_cast<int>(cfg[0]), static_cast<int>(cfg[1]), static_cast<int>(cfg[2]),
                      static_cast<int>(cfg[3]), static_cast<int>(cfg[4]), static_cast<int>(cfg[5]),
                      static_cast<int>(cfg[6]), static_cast<int>(cfg[7]), static_cast<int>(cfg[8]),
-                     static_cast<int>(cfg[9])};
+                     static_cast<int>(cfg[9]), cfg.size() == 11 ? static_cast<int>(cfg[10]) : 1, nullptr};
+  at::Tensor cyc = at::zeros({2}, a.options().dtype(at::kLong));
+  c.cycles = reinterpret_cast<unsigned long long*>(cyc.data_ptr());
   TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && a.scalar_type() == at::kBFloat16 &&
               b.scalar_type() == at::kBFloat16);
   TensorView va{nullptr, 0, 1, 128, 128}, vb{nullptr, 0, 1, 128, 128};
@@ -231,6 +243,7 @@ at::Tensor probe(const at::Tensor& a, const at::Tensor& b, std::vector<int64_t> 
   at::Tensor out = at::zeros({128, c.n}, a.options().dtype(at::kFloat));
   check(rfa::probe_launch(va, vb, a.data_ptr(), b.data_ptr(), out.data_ptr<float>(), c,
                           at::cuda::getCurrentCUDAStream()));
+  if (cfg.size() == 11) return cyc;  // throughput mode: (total cycles, issue cycles)
   return out;
 }
 
@@ -284,6 +297,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("dv_ptrs", &FusedCtx::dv_ptrs)
       .def_readwrite("dkv_targets", &FusedCtx::dkv_targets)
       .def_readwrite("dkv_wait_epoch", &FusedCtx::dkv_wait_epoch);
+  m.def("set_trace", &set_trace);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_fused", &attn_fwd_fused);
   m.def("attn_bwd_fused", &attn_bwd_fused);

@@ -95,6 +95,8 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const uint32_t idesc = umma_idesc_f16(1, 128, c.n, a_mn, b_mn);
     const uint32_t sa_u = smem_u32(sa), sb_u = smem_u32(sb);
     const int b_rows = c.b_kind == 0 ? c.n : c.kdim;  // rows of the B tile as stored
+    const long long t_start = clock64();
+    for (int rep = 0; rep < (c.reps > 0 ? c.reps : 1); ++rep)
     for (int k = 0; k < c.kdim / 16; ++k) {
       uint64_t bd;
       if (c.b_kind == 0) {
@@ -108,7 +110,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                             c.sbo_b >= 0 ? c.sbo_b : 1024, kSwizzle128B);
       }
       if (c.a_kind == 1) {
-        umma_ts(tmem, tmem + 256 + k * 8, bd, idesc, k > 0);
+        umma_ts(tmem, tmem + 256 + k * 8, bd, idesc, (k > 0 || rep > 0) ? 1u : 0u);
       } else {
         uint64_t ad;
         if (c.a_kind == 0) {
@@ -120,10 +122,16 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           ad = umma_smem_desc(sa_u + k * (c.kstep_a >= 0 ? c.kstep_a : 2048), c.lbo_a >= 0 ? c.lbo_a : 16384,
                               c.sbo_a >= 0 ? c.sbo_a : 1024, kSwizzle128B);
         }
-        umma_ss(tmem, ad, bd, idesc, k > 0);
+        umma_ss(tmem, ad, bd, idesc, (k > 0 || rep > 0) ? 1u : 0u);
       }
     }
+    const long long t_issued = clock64();
     umma_commit(&sm->done);
+    mbar_wait(&sm->done, 0);
+    if (c.cycles != nullptr) {
+      c.cycles[0] = static_cast<unsigned long long>(clock64() - t_start);
+      c.cycles[1] = static_cast<unsigned long long>(t_issued - t_start);
+    }
   }
   __syncwarp();
   mbar_wait(&sm->done, 0);
