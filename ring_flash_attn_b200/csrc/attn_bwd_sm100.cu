@@ -28,6 +28,18 @@
 namespace rfa {
 namespace bwd {
 
+#ifdef RFA_TRACE
+// per-tile stamps of CTA 0 (16 slots): 0-5 MMA warp, 6-10 softmax half 0, 11-12 drain
+#define RFA_STAMP(cond, iter, slot)                                                              \
+  do {                                                                                            \
+    if ((cond) && cta == 0 && p.trace != nullptr && (iter) < 64) p.trace[(iter)*16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define RFA_STAMP(cond, iter, slot) \
+  do {                              \
+  } while (0)
+#endif
+
 constexpr int kD = 128;
 constexpr int kTileK = 128;  // keys per CTA
 constexpr int kTileQ = 64;   // queries per inner iteration
@@ -252,11 +264,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int i = 0; i < total_tiles; ++i) {
           const uint32_t q_mn = q_mn0 + slot * stage_step;  // Q_i read MN-major (B of dK)
           const uint32_t do_mn = q_mn + do_step;            // dO_i read MN-major (B of dV)
+          RFA_STAMP(leader, i, 0);
           if (i + 1 < total_tiles && !(p.debug & 2)) issue_s();
+          RFA_STAMP(leader, i, 1);
           // dV += P^T dO   (P^T: bf16 in the first 32 columns of this tile's S^T buffer)
           mbar_wait(&bars->p_ready[i & 1], ph_p[i & 1]);
           ph_p[i & 1] ^= 1;
           tc_fence_after();
+          RFA_STAMP(leader, i, 2);
           if (leader)
 #pragma unroll
           for (int k = 0; k < kTileQ / 16; ++k)
@@ -266,6 +281,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&bars->ds_ready, ph_ds);
           ph_ds ^= 1;
           tc_fence_after();
+          RFA_STAMP(leader, i, 3);
           if (leader)
 #pragma unroll
           for (int k = 0; k < kTileQ / 16; ++k)
@@ -276,6 +292,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             ph_dqfree ^= 1;
             tc_fence_after();
           }
+          RFA_STAMP(leader, i, 4);
           if (leader) {
 #pragma unroll
             for (int k = 0; k < kTileK / 16; ++k)
@@ -298,6 +315,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
           if (i + 1 < total_tiles && (p.debug & 2)) issue_s();
+          RFA_STAMP(leader, i, 5);
           __syncwarp();
         }
         if (leader) umma_commit(&bars->dkv_done);
@@ -373,26 +391,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float4 v4 = *reinterpret_cast<const float4*>(st + c);
             lse2[c] = v4.x; lse2[c + 1] = v4.y; lse2[c + 2] = v4.z; lse2[c + 3] = v4.w;
           }
-          if (p.debug & 1) {
-            const int head = kv_head * group + gq;
-            for (int c = 0; c < 32; ++c) {
-              const int qi = ti * kTileQ + c0 + c;
-              float v = CUDART_INF_F;
-              if (qi < g.q_len) {
-                const int row = g.q_row0 + qi;
-                const size_t b = row / p.lse_S, sidx = row % p.lse_S;
-                const float x = p.lse[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx];
-                v = x == -CUDART_INF_F ? CUDART_INF_F : x * 1.4426950408889634f;
-              }
-              lse2[c] = v;
-            }
-          }
 
           const int buf = i & 1;
           const uint32_t t_s = tmem + kColS + buf * 64 + lane_addr;
           mbar_wait(&bars->s_full[buf], ph_s[buf]);
           ph_s[buf] ^= 1;
           tc_fence_after();
+          RFA_STAMP(threadIdx.x == 128, i, 6);
           uint32_t sr[32];
           tmem_ld32(t_s + c0, sr);
           tmem_ld_wait();
@@ -416,6 +421,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars->p_ready[buf]);
+          RFA_STAMP(threadIdx.x == 128, i, 7);
 
           // dS^T = P^T o (dP^T - delta) * scale  -> shared memory, 128-byte swizzled rows of 64 bf16
           float dlt[32];
@@ -424,22 +430,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float4 v4 = *reinterpret_cast<const float4*>(st + kTileQ + c);
             dlt[c] = v4.x; dlt[c + 1] = v4.y; dlt[c + 2] = v4.z; dlt[c + 3] = v4.w;
           }
-          if (p.debug & 1) {
-            const int head = kv_head * group + gq;
-            for (int c = 0; c < 32; ++c) {
-              const int qi = ti * kTileQ + c0 + c;
-              float v = 0.f;
-              if (qi < g.q_len) {
-                const int row = g.q_row0 + qi;
-                const size_t b = row / p.lse_S, sidx = row % p.lse_S;
-                v = p.delta[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx];
-              }
-              dlt[c] = v;
-            }
-          }
+
           mbar_wait(&bars->dp_full, ph_dp);
           ph_dp ^= 1;
           tc_fence_after();
+          RFA_STAMP(threadIdx.x == 128, i, 8);
           uint32_t dpr[32];
           tmem_ld32(tmem + kColDP + lane_addr + c0, dpr);
           tmem_ld_wait();
@@ -461,6 +456,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&bars->ds_ready);
+          RFA_STAMP(threadIdx.x == 128, i, 9);
         }
       }
     }
@@ -526,6 +522,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&bars->dq_full, ph);
           ph ^= 1;
           tc_fence_after();
+          RFA_STAMP(wg_tid == 0, i, 11);
           uint32_t r[64];
           tmem_ld32(tmem + kColDQ + lane_addr, r);
           tmem_ld32(tmem + kColDQ + lane_addr + 32, r + 32);
@@ -543,6 +540,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tma_reduce_add_3d(&tm_dq, smem_dq, 0, head, g.q_row0 + ti * kTileQ);
             tma_store_commit();
           }
+          RFA_STAMP(wg_tid == 0, i, 12);
         }
       }
     }

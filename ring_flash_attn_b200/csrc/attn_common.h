@@ -169,7 +169,8 @@ struct BwdParams {
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
   int n_items;
-  int debug;  // bisecting aid: bit0 = stats straight from global, bit1 = no S^T look-ahead
+  int debug;  // bisecting aid: bit1 = no S^T look-ahead
+  unsigned long long* trace;  // RFA_TRACE builds only
   PushParams push;
   SignalParams sig;
   DkvParams dkv;

@@ -162,6 +162,7 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
                  dq_accum.stride(1)};
   p.n_items = static_cast<int>(items.size(0));
   if (const char* e = std::getenv("RFA_B200_DEBUG")) p.debug = std::atoi(e);
+  p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);

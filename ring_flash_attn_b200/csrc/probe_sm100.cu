@@ -16,6 +16,33 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+// Throughput loop: warp-uniform control flow, constant-step descriptors, one elected lane issues - exactly the
+// issue pattern of the attention kernels - so the measured cycles are the tensor pipe's, not the issuer's.
+template <int A_KIND, int B_KIND, int N, int KSTEPS>
+__device__ __forceinline__ void rate_loop(uint32_t tmem, uint32_t sa_u, uint32_t sb_u, int reps, bool leader) {
+  constexpr uint32_t hi = umma_desc_hi(1024, kSwizzle128B);
+  constexpr int b_rows = B_KIND == 0 ? N : KSTEPS * 16;
+  constexpr uint32_t idesc = umma_idesc_f16(1, 128, N, A_KIND == 3, B_KIND != 0);
+  const uint32_t b0 = umma_desc_lo(sb_u, B_KIND == 1 ? b_rows * 128 : 16);
+  const uint32_t a0 = A_KIND == 1 ? tmem + 256 : umma_desc_lo(sa_u, A_KIND == 3 ? 16384 : 16);
+  for (int rep = 0; rep < reps; ++rep) {
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        const uint32_t bo = B_KIND == 0 ? (((k >> 2) * (b_rows * 128) + (k & 3) * 32) >> 4) : (k * 2048) >> 4;
+        if constexpr (A_KIND == 1) {
+          umma_ts2(tmem, a0 + k * 8, b0 + bo, hi, idesc, 1u);
+        } else {
+          const uint32_t ao = A_KIND == 0 ? (((k >> 2) * 16384 + (k & 3) * 32) >> 4)
+                                          : (A_KIND == 2 ? (k * 32) >> 4 : (k * 2048) >> 4);
+          umma_ss2(tmem, a0 + ao, hi, b0 + bo, hi, idesc, 1u);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // operand kinds
 //  A: 0 = smem K-major [128 rows][128 k] via TMA      (Q/K/V as A)
 //     1 = TMEM bf16 [128 rows][kdim]                   (P, P^T)
@@ -72,7 +99,32 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
 
-  if (tid == 0) {
+  if (c.reps > 1 && warp == 0) {
+    // all operands were staged by threads / are garbage-tolerant: only timing matters here
+    const bool leader = elect_one();
+    const uint32_t sa_u = smem_u32(sa), sb_u = smem_u32(sb);
+    const long long t0 = clock64();
+    const int form = c.a_kind * 100 + c.b_kind * 10 + (c.n == 128 ? 1 : 0) + (c.kdim == 128 ? 2 : 0);
+    switch (form) {
+      case 3: rate_loop<0, 0, 128, 8>(tmem, sa_u, sb_u, c.reps, leader); break;    // QK
+      case 2: rate_loop<0, 0, 64, 8>(tmem, sa_u, sb_u, c.reps, leader); break;     // S^T
+      case 113: rate_loop<1, 1, 128, 8>(tmem, sa_u, sb_u, c.reps, leader); break;  // PV
+      case 111: rate_loop<1, 1, 128, 4>(tmem, sa_u, sb_u, c.reps, leader); break;  // dV
+      case 211: rate_loop<2, 1, 128, 4>(tmem, sa_u, sb_u, c.reps, leader); break;  // dK
+      case 322: rate_loop<3, 2, 64, 8>(tmem, sa_u, sb_u, c.reps, leader); break;   // dQ^T
+      default: break;
+    }
+    const long long t1 = clock64();
+    if (leader) umma_commit(&sm->done);
+    __syncwarp();
+    mbar_wait(&sm->done, 0);
+    if (leader && c.cycles != nullptr) {
+      c.cycles[0] = static_cast<unsigned long long>(clock64() - t0);
+      c.cycles[1] = static_cast<unsigned long long>(t1 - t0);
+    }
+  } else if (c.reps > 1) {
+    // other warps just wait for the epilogue
+  } else if (tid == 0) {
     uint32_t bytes = 0;
     if (c.a_kind == 0 || c.a_kind == 3) bytes += 32768;
     if (c.b_kind == 0) bytes += c.n * 256;
@@ -95,6 +147,38 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const uint32_t idesc = umma_idesc_f16(1, 128, c.n, a_mn, b_mn);
     const uint32_t sa_u = smem_u32(sa), sb_u = smem_u32(sb);
     const int b_rows = c.b_kind == 0 ? c.n : c.kdim;  // rows of the B tile as stored
+    if (c.reps > 1) {
+      // throughput mode: descriptors precomputed, instructions issued back to back (what the kernels do)
+      constexpr uint32_t hi = umma_desc_hi(1024, kSwizzle128B);
+      uint32_t a_lo[8], b_lo[8];
+      const int ksteps = c.kdim / 16;
+      for (int k = 0; k < ksteps; ++k) {
+        if (c.b_kind == 0) b_lo[k] = umma_desc_lo(sb_u + (k >> 2) * (b_rows * 128) + (k & 3) * 32, 16);
+        else if (c.b_kind == 1) b_lo[k] = umma_desc_lo(sb_u + k * 2048, b_rows * 128);
+        else b_lo[k] = umma_desc_lo(sb_u + k * 2048, 16);
+        if (c.a_kind == 0) a_lo[k] = umma_desc_lo(sa_u + (k >> 2) * 16384 + (k & 3) * 32, 16);
+        else if (c.a_kind == 2) a_lo[k] = umma_desc_lo(sa_u + k * 32, 16);
+        else if (c.a_kind == 3) a_lo[k] = umma_desc_lo(sa_u + k * 2048, 16384);
+        else a_lo[k] = tmem + 256 + k * 8;
+      }
+      const long long t0 = clock64();
+      for (int rep = 0; rep < c.reps; ++rep) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < ksteps) {
+            if (c.a_kind == 1) umma_ts2(tmem, a_lo[k], b_lo[k], hi, idesc, 1u);
+            else umma_ss2(tmem, a_lo[k], hi, b_lo[k], hi, idesc, 1u);
+          }
+        }
+      }
+      const long long t1 = clock64();
+      umma_commit(&sm->done);
+      mbar_wait(&sm->done, 0);
+      if (c.cycles != nullptr) {
+        c.cycles[0] = static_cast<unsigned long long>(clock64() - t0);
+        c.cycles[1] = static_cast<unsigned long long>(t1 - t0);
+      }
+    } else {
     const long long t_start = clock64();
     for (int rep = 0; rep < (c.reps > 0 ? c.reps : 1); ++rep)
     for (int k = 0; k < c.kdim / 16; ++k) {
@@ -131,6 +215,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     if (c.cycles != nullptr) {
       c.cycles[0] = static_cast<unsigned long long>(clock64() - t_start);
       c.cycles[1] = static_cast<unsigned long long>(t_issued - t_start);
+    }
     }
   }
   __syncwarp();
