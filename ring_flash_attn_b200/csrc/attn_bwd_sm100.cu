@@ -168,7 +168,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (lane == 0) {
         const bool staged = it.flag >= 0 && p.ready_flags != nullptr;
         if (staged) {
-          wait_epoch(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready");
+          wait_epoch(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready", p.sig.my_rank, it.flag);
           fence_proxy_async_all();
         }
         const CUtensorMap* mk = staged ? &tm_ks : &tm_k;
@@ -465,7 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int row = (remote ? it.out_row0 : it.kv_row0) + key;
     if (remote && wg_tid == 0) {
       // the owner must have drained what we stored into its inbox during the previous backward call
-      wait_epoch(p.dkv.my_pad + kPadInboxFree + it.owner, p.dkv.wait_epoch, "inbox reuse");
+      wait_epoch(p.dkv.my_pad + kPadInboxFree + it.owner, p.dkv.wait_epoch, "inbox reuse", p.dkv.my_rank, it.owner);
     }
     if (remote) named_bar_sync(1 + half, 128);
     if (total_tiles > 0) {

@@ -19,6 +19,8 @@
 #include <math_constants.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "attn_common.h"
 #include "comm_device.cuh"
 #include "sm100_ptx.cuh"
@@ -48,6 +50,7 @@ constexpr int kThreads = 384;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays below 2^8
+constexpr int kPolyOf4 = 2;                // of every 4 element pairs, this many use the polynomial exp2
 
 struct Barriers {
   uint64_t q_full[2];
@@ -164,7 +167,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const SegGeom g = seg_geom(sg, it);
         const bool staged = sg.flag >= 0 && p.ready_flags != nullptr;
         if (g.n_tiles > 0 && staged) {
-          wait_epoch(p.ready_flags + sg.flag, p.ready_epoch, "fwd kv ready");
+          wait_epoch(p.ready_flags + sg.flag, p.ready_epoch, "fwd kv ready", p.sig.my_rank, sg.flag);
           fence_proxy_async_all();
         }
         for (int jj = 0; jj < g.n_tiles; ++jj) {
@@ -366,7 +369,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < 128; ++c) s[c] = __uint_as_float(sr[c]);
 
-          if (tile_needs_mask(g, it, t, jj)) {
+          const bool masked = tile_needs_mask(g, it, t, jj);
+          if (masked) {
             long long lim_ll = static_cast<long long>(chunk_row) + g.diag;
             if (lim_ll > g.kv_len - 1) lim_ll = g.kv_len - 1;
             lim_ll -= static_cast<long long>(jj) * kTile;
@@ -407,22 +411,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           first = false;
           const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * p.scale_log2;
-          float l0 = 0.f, l1 = 0.f;
           turn_wait();
           RFA_STAMP(stamper, xi, 8 + 5 * t);
+          // exp2(s * c - m * c) on packed pairs.  MUFU.EX2 alone (16 lanes per SM) would cost 1024 cycles per
+          // 128x128 tile per warp and bound the whole kernel, so kPolyOf4 of every 4 pairs are evaluated with
+          // a polynomial on the FMA pipes instead (masked tiles keep exact zeros by staying on the MUFU path).
+          const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nmc2 = pack2(-mc, -mc);
+          uint64_t lsum = pack2(0.f, 0.f);
+          auto exp_chunks = [&](auto use_poly) {
 #pragma unroll
-          for (int c = 0; c < 128; c += 32) {
-            uint32_t pk[16];
+            for (int c = 0; c < 128; c += 32) {
+              uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float e0 = fast_exp2(fmaf(s[c + 2 * i], p.scale_log2, -mc));
-              const float e1 = fast_exp2(fmaf(s[c + 2 * i + 1], p.scale_log2, -mc));
-              l0 += e0;
-              l1 += e1;
-              pk[i] = Pack2<T>::pack(e0, e1);
+              for (int i = 0; i < 16; ++i) {
+                const uint64_t x = ffma2(pack2(s[c + 2 * i], s[c + 2 * i + 1]), sc2, nmc2);
+                float e0, e1;
+                if (decltype(use_poly)::value && (i & 3) < kPolyOf4) {
+                  exp2_poly2(x, e0, e1);
+                } else {
+                  float x0, x1;
+                  unpack2(x, x0, x1);
+                  e0 = fast_exp2(x0);
+                  e1 = fast_exp2(x1);
+                }
+                lsum = fadd2(lsum, pack2(e0, e1));
+                pk[i] = Pack2<T>::pack(e0, e1);
+              }
+              tmem_st16(t_s + (c >> 1), pk);
             }
-            tmem_st16(t_s + (c >> 1), pk);
+          };
+          if (masked) {
+            exp_chunks(std::false_type{});
+          } else {
+            exp_chunks(std::true_type{});
           }
+          float l0, l1;
+          unpack2(lsum, l0, l1);
           turn_pass();
           RFA_STAMP(stamper, xi, 9 + 5 * t);
           l += l0 + l1;

@@ -23,12 +23,14 @@ namespace rfa {
 __device__ __forceinline__ bool epoch_reached(uint32_t have, uint32_t want) {
   return static_cast<int32_t>(have - want) >= 0;
 }
-__device__ __forceinline__ void wait_epoch(const uint32_t* flag, uint32_t want, const char* what) {
+__device__ __forceinline__ void wait_epoch(const uint32_t* flag, uint32_t want, const char* what, int who = -1,
+                                           int idx = -1) {
   if (epoch_reached(ld_acquire_sys(flag), want)) return;
   const uint64_t t0 = global_timer_ns();
   while (!epoch_reached(ld_acquire_sys(flag), want)) {
     if (global_timer_ns() - t0 > RFA_WATCHDOG_NS) {
-      printf("rfa: epoch wait timeout (%s) block %d want %u have %u\n", what, blockIdx.x, want, ld_acquire_sys(flag));
+      printf("rfa: epoch wait timeout (%s) rank %d peer/flag %d block %d want %u have %u\n", what, who, idx,
+             blockIdx.x, want, ld_acquire_sys(flag));
       __trap();
     }
   }
@@ -53,7 +55,7 @@ __device__ __forceinline__ void push_role(const PushParams& pp) {
     const PushTask t = pp.tasks[ti];
     if (tid == 0 && pp.epoch > 2) {
       // the destination must have finished reading what we pushed into this staging parity two calls ago
-      wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse");
+      wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse", pp.my_rank, t.dst);
     }
     __syncthreads();
     const int vec_per_row = pp.row_bytes >> 4;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     for (int r = 0; r < p.world; ++r) {
       if ((t.src_mask >> r) & 1u) {
-        if (r != p.my_rank) wait_epoch(p.my_pad + kPadDkvReady + r, p.epoch, "dkv landed");
+        if (r != p.my_rank) wait_epoch(p.my_pad + kPadDkvReady + r, p.epoch, "dkv landed", p.my_rank, r);
       }
     }
   }

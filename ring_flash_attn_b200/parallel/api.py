@@ -80,26 +80,29 @@ def _scale(q, softmax_scale):
     return q.shape[-1] ** (-0.5) if softmax_scale is None else float(softmax_scale)
 
 
-_CU_CACHE = {}
-# (cu_q, cu_k, k_start, rank, world, causal) -> global cu_seqlens, filled by prepare(); lets a rank derive its
-# peers' llama3 plans locally (needed by the fused path to know which K/V rows each peer wants).
-_LLAMA3_GLOBAL = {}
+# The llama3 entry point only receives this rank's slice description; different global layouts can produce the
+# SAME local description on some rank, so prepare() attaches the global cu_seqlens to the tensor objects it
+# returns (attribute `_rfa_llama3`) and the entry point reads it back from the tensors the caller passes in.
+# It lets a rank derive its peers' plans locally - the fused path must know which K/V rows each peer wants.
 
 
 def cu_seqlens_to_host(cu: torch.Tensor) -> Tuple[int, ...]:
-    """Host copy of a cu_seqlens tensor; device tensors are read once per (storage, version)."""
+    """Host copy of a cu_seqlens tensor.  A device tensor is read back once; the result is remembered ON the
+    tensor object together with its version counter (never keyed by address: the caching allocator hands the
+    same address to the next batch's cu_seqlens)."""
     if not isinstance(cu, torch.Tensor):
         return tuple(int(x) for x in cu)
     if cu.device.type == "cpu":
         return tuple(int(x) for x in cu.tolist())
-    key = (cu.data_ptr(), cu._version, cu.numel(), cu.device.index)
-    hit = _CU_CACHE.get(key)
-    if hit is None:
-        if len(_CU_CACHE) > 256:
-            _CU_CACHE.clear()
-        hit = tuple(int(x) for x in cu.tolist())
-        _CU_CACHE[key] = hit
-    return hit
+    cached = getattr(cu, "_rfa_host", None)
+    if cached is not None and cached[0] == cu._version:
+        return cached[1]
+    vals = tuple(int(x) for x in cu.tolist())
+    try:
+        cu._rfa_host = (cu._version, vals)
+    except AttributeError:  # pragma: no cover - exotic tensor subclasses
+        pass
+    return vals
 
 
 @functools.lru_cache(maxsize=512)
@@ -123,7 +126,9 @@ def _varlen_plan(scheme, rank, world, cu, causal):
 
 
 @functools.lru_cache(maxsize=512)
-def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal):
+def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=None):
+    # global_cu is part of the cache key on purpose: plans with equal local content but different global
+    # layouts must not share their per-plan caches (peers' needs, push tables)
     return P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal)
 
 
@@ -266,11 +271,10 @@ def llama3_flash_attn_prepare_cu_seqlens(cu_seqlens: torch.Tensor, causal: bool,
     dt = cu_seqlens.dtype if isinstance(cu_seqlens, torch.Tensor) else torch.int32
     cu_q_t = torch.tensor(cu_q, dtype=dt, device=dev)
     cu_k_t = torch.tensor(cu_k, dtype=dt, device=dev)
-    _CU_CACHE[(cu_q_t.data_ptr(), cu_q_t._version, cu_q_t.numel(), cu_q_t.device.index)] = tuple(cu_q)
-    _CU_CACHE[(cu_k_t.data_ptr(), cu_k_t._version, cu_k_t.numel(), cu_k_t.device.index)] = tuple(cu_k)
-    if len(_LLAMA3_GLOBAL) > 1024:
-        _LLAMA3_GLOBAL.clear()
-    _LLAMA3_GLOBAL[(tuple(cu_q), tuple(cu_k), slice_left, rank, world_size, bool(causal))] = tuple(cu)
+    cu_q_t._rfa_host = (cu_q_t._version, tuple(cu_q))
+    cu_k_t._rfa_host = (cu_k_t._version, tuple(cu_k))
+    # remember the global layout ON the returned tensor objects (see _LLAMA3_GLOBAL note above)
+    cu_q_t._rfa_llama3 = cu_k_t._rfa_llama3 = (tuple(cu), tuple(cu_q), tuple(cu_k), rank, world_size, bool(causal))
     max_q = max(b - a for a, b in zip(cu_q[:-1], cu_q[1:]))
     max_k = max(b - a for a, b in zip(cu_k[:-1], cu_k[1:]))
     return cu_q_t, cu_k_t, max_q, max_k, slice(slice_left, slice_right)
@@ -280,7 +284,7 @@ def llama3_flash_attn_prepare_cu_seqlens(cu_seqlens: torch.Tensor, causal: bool,
 def _llama3_peer_plan(global_cu, causal, rank, world, tokens):
     cq, ck, _mq, _mk, ks = llama3_flash_attn_prepare_cu_seqlens(torch.tensor(global_cu, dtype=torch.int32), causal,
                                                                rank, world)
-    return _llama3_plan(rank, world, tokens, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), causal)
+    return _llama3_plan(rank, world, tokens, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), causal, global_cu)
 
 
 def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
@@ -293,10 +297,18 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
     rank, world = group_info(group)
     k_start = local_k_slice.start or 0
     cu_q_host, cu_k_host = cu_seqlens_to_host(cu_seqlens_q), cu_seqlens_to_host(cu_seqlens_k)
-    plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal))
-    glob = _LLAMA3_GLOBAL.get((cu_q_host, cu_k_host, int(k_start), rank, world, bool(causal)))
+    glob = None
+    hit = getattr(cu_seqlens_q, "_rfa_llama3", None)
+    if hit is not None and hit is getattr(cu_seqlens_k, "_rfa_llama3", None) and \
+            hit[1:] == (cu_q_host, cu_k_host, rank, world, bool(causal)):
+        glob = hit[0]
+    plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal), glob)
     if glob is not None:
         plan.peer = lambda r, _g=glob, _w=world, _c=bool(causal), _t=q.shape[0]: _llama3_peer_plan(_g, _c, r, _w, _t)
+    elif world > 1:
+        # global layout unknown (cu tensors not produced by prepare()): the peers' needs cannot be derived
+        # locally, so this call uses the torch.distributed all-gather transport around the same kernels
+        plan.fused_ok = False
     out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
                                  int(heads_k_stride), deterministic)
     return (out, lse, None) if return_attn_probs else out

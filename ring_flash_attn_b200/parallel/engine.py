@@ -236,8 +236,10 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 # entry points used by the autograd bridge
 # ----------------------------------------------------------------------------------------------
 
-def _fused_ok(q: torch.Tensor, k: torch.Tensor, group) -> bool:
+def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
     if not _use_cuda_kernels(q, k):
+        return False
+    if plan is not None and not getattr(plan, "fused_ok", True):
         return False
     from . import fused
 
@@ -245,7 +247,7 @@ def _fused_ok(q: torch.Tensor, k: torch.Tensor, group) -> bool:
 
 
 def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_stride: int = 1):
-    if _fused_ok(q, k, group):
+    if _fused_ok(q, k, group, plan):
         from . import fused
 
         return fused.forward(plan, q, k, v, scale, group)
@@ -256,7 +258,7 @@ def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_st
 
 def cp_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, transport="ring",
                 heads_k_stride: int = 1, deterministic: bool = False):
-    if _fused_ok(q, k, group):
+    if _fused_ok(q, k, group, plan):
         from . import fused
 
         return fused.backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)

@@ -38,7 +38,10 @@ def run_distributed(fn, world, *args, backend="gloo"):
         for p in procs:
             if p.is_alive():
                 p.kill()
-        if not err_q.empty():
-            rank, tb = err_q.get()
-            raise AssertionError(f"rank {rank} failed:\n{tb}")
+        errs = []
+        while not err_q.empty():
+            errs.append(err_q.get())
+        if errs:
+            errs.sort()
+            raise AssertionError("\n".join(f"rank {r} failed:\n{tb}" for r, tb in errs))
         assert not failed, f"{len(failed)} worker(s) exited abnormally"

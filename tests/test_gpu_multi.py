@@ -80,6 +80,17 @@ def _more_gpus(rank, world):
         _varlen_case(rank, world, which, True)
 
 
+def _llama3_only(rank, world):
+    _varlen_case(rank, world, "llama3", True)
+
+
+@pytest.mark.parametrize("world", [8])
+def test_llama3_fused_8gpu(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    run_distributed(_llama3_only, world, backend="nccl")
+
+
 @pytest.mark.parametrize("world", [4, 8])
 def test_fused_more_gpus(world):
     if _ngpu() < world:
