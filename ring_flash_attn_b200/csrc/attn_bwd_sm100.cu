@@ -100,7 +100,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ BwdParams p) {
   // communication CTAs first (see comm_device.cuh): they re-publish this rank's K/V rows to the peers
   if (static_cast<int>(blockIdx.x) < p.push.n_ctas) {
-    push_role(p.push);
+    if (p.push.use_tma) {
+      extern __shared__ uint8_t push_smem_raw[];
+      push_role_tma(p.push, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(push_smem_raw) + 1023) & ~uintptr_t(1023)));
+    } else {
+      push_role(p.push);
+    }
     return;
   }
   const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;

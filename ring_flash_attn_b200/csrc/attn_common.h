@@ -61,6 +61,7 @@ struct PushParams {
   int n_ctas;     // blocks [0, n_ctas) of the grid are push CTAs
   int row_bytes;  // bytes per staged row (kv heads * 128 * 2)
   int my_rank;
+  int use_tma;    // 1: bulk-copy (TMA) push, 0: LSU copy loop
   uint32_t epoch;
   long long parity_off;         // byte offset of the staging half used by this call
   const char* src_base[2];      // local K / V

@@ -19,6 +19,7 @@
 #include <math_constants.h>
 #include <stdio.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "attn_common.h"
@@ -26,6 +27,8 @@
 #include "sm100_ptx.cuh"
 
 namespace rfa {
+
+constexpr int kDefaultPolyOf4 = 0;  // measured on B200: see profiles/ (MUFU-only is the fastest so far)
 
 namespace fwd {
 
@@ -50,7 +53,6 @@ constexpr int kThreads = 384;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays below 2^8
-constexpr int kPolyOf4 = 2;                // of every 4 element pairs, this many use the polynomial exp2
 
 struct Barriers {
   uint64_t q_full[2];
@@ -96,7 +98,8 @@ __device__ __forceinline__ bool tile_needs_mask(const SegGeom& g, const WorkItem
   return ragged || diagonal;
 }
 
-template <typename T>
+// kPolyOf4: of every 4 element pairs, this many use the polynomial exp2 (0 = MUFU only)
+template <typename T, int kPolyOf4>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_ks,
@@ -104,7 +107,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // The first blocks of the grid are communication CTAs: they push this rank's K/V rows to the peers that
   // need them while the remaining (compute) CTAs already work on the local shard.
   if (static_cast<int>(blockIdx.x) < p.push.n_ctas) {
-    push_role(p.push);
+    if (p.push.use_tma) {
+      extern __shared__ uint8_t push_smem_raw[];
+      push_role_tma(p.push, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(push_smem_raw) + 1023) & ~uintptr_t(1023)));
+    } else {
+      push_role(p.push);
+    }
     return;
   }
   const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;
@@ -515,18 +523,26 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
   if (const char* e = make_tensor_map(&tks, k_stage, 2, fwd::kTile, fwd::kD)) return e;
   if (const char* e = make_tensor_map(&tvs, v_stage, 2, fwd::kTile, fwd::kD)) return e;
   dim3 grid(n_blocks, 1, 1), block(fwd::kThreads, 1, 1);
-  cudaError_t err;
+  cudaError_t err = cudaSuccess;
+  static const int poly = [] {
+    const char* e = std::getenv("RFA_B200_POLY_EXP");
+    const int v = e ? std::atoi(e) : kDefaultPolyOf4;
+    return v < 0 ? 0 : (v > 2 ? 2 : v);
+  }();
+  auto launch = [&](auto kern) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    if (err == cudaSuccess) kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
+  };
   if (dtype == kDtypeBF16) {
-    auto kern = fwd::attn_fwd_kernel<__nv_bfloat16>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
-    if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
+    if (poly == 0) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0>);
+    else if (poly == 1) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 1>);
+    else launch(fwd::attn_fwd_kernel<__nv_bfloat16, 2>);
   } else {
-    auto kern = fwd::attn_fwd_kernel<__half>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
-    if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
+    if (poly == 0) launch(fwd::attn_fwd_kernel<__half, 0>);
+    else if (poly == 1) launch(fwd::attn_fwd_kernel<__half, 1>);
+    else launch(fwd::attn_fwd_kernel<__half, 2>);
   }
+  if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

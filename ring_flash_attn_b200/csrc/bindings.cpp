@@ -53,6 +53,12 @@ void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, co
   pp.n_ctas = pp.n_tasks > 0 ? static_cast<int>(c.n_push_ctas) : 0;
   pp.row_bytes = static_cast<int>(c.row_bytes);
   pp.my_rank = static_cast<int>(c.my_rank);
+  {
+    const char* e = std::getenv("RFA_B200_PUSH_TMA");
+    pp.use_tma = e ? std::atoi(e) : 1;
+    // bulk copies need 16-byte aligned rows on both sides
+    if ((c.row_bytes % 16) || ((k.stride(0) * k.element_size()) % 16) || ((v.stride(0) * v.element_size()) % 16)) pp.use_tma = 0;
+  }
   pp.epoch = static_cast<uint32_t>(c.epoch);
   pp.parity_off = c.parity_off;
   pp.src_base[0] = static_cast<const char*>(k.data_ptr());

@@ -94,6 +94,82 @@ __device__ __forceinline__ void push_role(const PushParams& pp) {
   }
 }
 
+// ---- TMA variant of the push role -----------------------------------------------------------------------
+// One thread drives bulk copies local HBM -> shared memory -> peer HBM through a ring of 32 KB buffers, so a
+// single CTA keeps ~100 KB of loads and ~100 KB of NVLink stores in flight (the LSU loop above is limited to
+// the 48 KB its threads can hold in registers and measured only ~16 GB/s per CTA).
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+constexpr int kPushBufBytes = 32768;
+constexpr int kPushBufs = 6;
+constexpr int kPushDepth = 3;  // loads in flight; with 6 buffers at most 2 store groups may still be reading
+
+__device__ __forceinline__ void push_role_tma(const PushParams& pp, uint8_t* smem) {
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPushBufs * kPushBufBytes);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPushBufs; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int rows_per_piece = pp.row_bytes >= kPushBufBytes ? 1 : kPushBufBytes / pp.row_bytes;
+  uint32_t n_loaded = 0, n_stored = 0;  // global piece counters (ring position / parity)
+  for (int ti = blockIdx.x; ti < pp.n_tasks; ti += pp.n_ctas) {
+    const PushTask t = pp.tasks[ti];
+    if (pp.epoch > 2) wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse", pp.my_rank, t.dst);
+    const long long pitch = pp.src_row_bytes[t.which];
+    const char* src = pp.src_base[t.which] + t.src_row * pitch;
+    char* dst = pp.stage_ptrs[t.dst] + pp.parity_off + t.dst_off;
+    const int pieces = (t.rows + rows_per_piece - 1) / rows_per_piece;
+    int ld = 0, stv = 0;
+    while (stv < pieces) {
+      while (ld < pieces && ld - stv < kPushDepth) {
+        const uint32_t slot = n_loaded % kPushBufs;
+        if (n_loaded >= kPushBufs) tma_store_wait_read<2>();  // the store that last used this buffer is done reading
+        const int r0 = ld * rows_per_piece;
+        const int nr = min(rows_per_piece, t.rows - r0);
+        uint8_t* buf = smem + slot * kPushBufBytes;
+        mbar_arrive_expect_tx(&bars[slot], static_cast<uint32_t>(nr) * pp.row_bytes);
+        if (pitch == pp.row_bytes) {
+          bulk_load(buf, src + static_cast<long long>(r0) * pitch, static_cast<uint32_t>(nr) * pp.row_bytes, &bars[slot]);
+        } else {
+          for (int r = 0; r < nr; ++r)
+            bulk_load(buf + r * pp.row_bytes, src + static_cast<long long>(r0 + r) * pitch, pp.row_bytes, &bars[slot]);
+        }
+        ++n_loaded;
+        ++ld;
+      }
+      const uint32_t slot = n_stored % kPushBufs;
+      mbar_wait(&bars[slot], (n_stored / kPushBufs) & 1);
+      const int r0 = stv * rows_per_piece;
+      const int nr = min(rows_per_piece, t.rows - r0);
+      bulk_store(dst + static_cast<long long>(r0) * pp.row_bytes, smem + slot * kPushBufBytes,
+                 static_cast<uint32_t>(nr) * pp.row_bytes);
+      tma_store_commit();
+      ++n_stored;
+      ++stv;
+    }
+    tma_store_wait<0>();  // every byte of this task has been written
+    fence_proxy_async_all();
+    __threadfence_system();
+    const uint32_t old = atomicAdd(pp.sent_count + t.dst, 1u);
+    if (old + 1u == pp.sent_target[t.dst]) {
+      __threadfence_system();
+      st_release_sys(pp.peer_pads[t.dst] + kPadKvReady + pp.my_rank, pp.epoch);
+    }
+  }
+}
+
 // Called by one thread of every compute CTA after the CTA has finished reading staged K/V.
 __device__ __forceinline__ void consumer_done(const SignalParams& sp) {
   if (sp.peer_pads == nullptr) return;
