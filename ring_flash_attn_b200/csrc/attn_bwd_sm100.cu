@@ -477,7 +477,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(&bars->dkv_done, 0);
       tc_fence_after();
     }
-    {
+    const bool bulk = remote && p.dkv.bulk != 0 && total_tiles > 0;
+    if (bulk) {
+      // Experimental (RFA_B200_DKV_BULK=1, off by default until validated on hardware): stage the fp32 tile
+      // row-major in shared memory that is idle by now (K|V for dK, the first two Q/dO stages for dV) and let one
+      // thread send each 512-byte row with cp.async.bulk, instead of one 16-byte NVLink store per lane and row.
+      const int which = half;
+      float* stage = reinterpret_cast<float*>(which == 0 ? smem_k : smem_qdo);
+      const uint32_t col = tmem + (which == 0 ? kColDK : kColDV) + lane_addr;
+      float* mine = stage + key * kD;
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(col + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<uint4*>(mine + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (wg_tid == 0) {
+        float* base = which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner];
+        char* g = reinterpret_cast<char*>(base + (static_cast<size_t>(it.out_row0) * p.hkv + kv_head) * kD);
+        const size_t gstride = static_cast<size_t>(p.hkv) * kD * sizeof(float);
+        for (int rr = 0; rr < it.kv_rows; ++rr) bulk_store(g + rr * gstride, stage + rr * kD, kD * sizeof(float));
+        tma_store_commit();
+        tma_store_wait<0>();
+        fence_proxy_async_all();
+      }
+    } else {
       const int which = half;
       float* base = remote ? (which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner])
                            : (which == 0 ? p.dk : p.dv);

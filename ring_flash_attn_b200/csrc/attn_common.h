@@ -92,6 +92,7 @@ struct DkvParams {
   uint32_t sent_target[kMaxRanks];
   uint32_t epoch;
   uint32_t wait_epoch;  // epoch of the previous backward call: owners must have reduced it before we overwrite
+  int bulk;             // experimental: stage tiles in smem and send rows with cp.async.bulk (default 0)
   int world;  // 0 = disabled: write to BwdParams::dk / dv
   int my_rank;
 };

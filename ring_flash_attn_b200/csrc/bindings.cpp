@@ -178,6 +178,13 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
     p.dkv.sent_count = cnt + 32;
     p.dkv.epoch = static_cast<uint32_t>(fc->epoch);
     p.dkv.wait_epoch = static_cast<uint32_t>(fc->dkv_wait_epoch);
+    {
+      static const int bulk = [] {
+        const char* e = std::getenv("RFA_B200_DKV_BULK");
+        return e ? std::atoi(e) : 0;
+      }();
+      p.dkv.bulk = bulk;
+    }
     p.dkv.world = static_cast<int>(fc->world);
     p.dkv.my_rank = static_cast<int>(fc->my_rank);
     for (int r = 0; r < fc->world; ++r) {

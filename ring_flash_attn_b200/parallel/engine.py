@@ -2,9 +2,10 @@
 
 Two transports, selected per call:
 
-* ``fused``   - sm_100a kernels; K/V shards are pulled from the owners' peer-mapped memory inside
-                the attention kernel itself and dK/dV partials are pushed back the same way
-                (``parallel/fused.py``).  Used whenever the tensors live on a Blackwell GPU.
+* ``fused``   - sm_100a kernels; the attention kernel's own communication CTAs push the K/V rows each
+                peer needs into that peer's memory over NVLink, and the backward stores dK/dV partials
+                straight into the owner's inbox (``parallel/fused.py`` / ``parallel/symm.py``).  Used
+                whenever the tensors live on Blackwell GPUs of one node with peer access.
 * ``ring`` / ``allgather`` - torch.distributed fallback (gloo on CPU, NCCL on GPUs without peer
                 access): the reference's own communication pattern
                 (/root/reference/ring_flash_attn/ring_flash_attn.py:26-63,97-152 and

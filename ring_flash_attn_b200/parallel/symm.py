@@ -10,8 +10,8 @@ rank of the group maps (``csrc/peer_mem.cpp``):
                        rank's shard, stored there by the peers' backward kernels.
 
 A forward is ONE launch of ``attn_fwd_kernel``: its first CTAs push this rank's K/V rows to the peers that
-need them (ring order, posted NVLink stores), the rest run the math and only wait on a source's "landed"
-flag when they reach that source's segments.  A backward is ``delta`` + ONE launch of ``attn_bwd_kernel``
+need them (ring order; TMA bulk copies HBM -> shared memory -> peer HBM), the rest run the math and only wait on
+a source's "landed" flag when they reach that source's segments.  A backward is ``delta`` + ONE launch of ``attn_bwd_kernel``
 (same push CTAs; dK/dV tiles are stored straight into the owners' inboxes) + the owner-side reduction.
 No NCCL call is on these paths; NCCL is used once, to exchange the IPC handles.
 
@@ -146,6 +146,19 @@ class PeerContext:
         self.done_cum = (self.done_cum + n_compute_ctas) & MASK32
         fc.done_target = self.done_cum
         return fc
+
+
+def destroy_peer_contexts() -> None:
+    """Unmap and free every peer buffer (collective: call on all ranks, e.g. before destroy_process_group)."""
+    for ctx in list(_CONTEXTS.values()):
+        if ctx is None:
+            continue
+        ctx._quiesce()
+        for buf in (ctx.stage, ctx.inbox, ctx.pad):
+            if buf is not None:
+                buf.close()
+        ctx.stage = ctx.inbox = None
+    _CONTEXTS.clear()
 
 
 def peer_context(group, device: torch.device) -> Optional[PeerContext]:
