@@ -63,14 +63,23 @@ def _batch_case(rank, world, scheme, causal, packing, hq, hkv, dtype):
     torch.testing.assert_close(gv.float(), shard(vr.grad, rank, world).float(), **tol)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("scheme,causal,packing,hq,hkv", [
+BATCH_CASES = [
     ("ring", True, "qkv", 4, 4), ("ring", False, "kv", 4, 2), ("ring", True, "none", 4, 1),
     ("zigzag", True, "qkv", 4, 4), ("zigzag", True, "kv", 6, 2), ("zigzag", True, "none", 2, 2),
     ("stripe", True, "qkv", 4, 4), ("stripe", True, "kv", 4, 2), ("stripe", True, "none", 3, 3),
-])
-def test_batch_schemes(world, scheme, causal, packing, hq, hkv):
-    run_distributed(_batch_case, world, scheme, causal, packing, hq, hkv, torch.float32)
+]
+
+
+def _all_batch_cases(rank, world):
+    # one process group per world size: spawning + rendezvous dominates the run time otherwise
+    for scheme, causal, packing, hq, hkv in BATCH_CASES:
+        _batch_case(rank, world, scheme, causal, packing, hq, hkv, torch.float32)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_batch_schemes(world):
+    """9 cases: {ring, zigzag, stripe} x {qkvpacked, kvpacked, unpacked} incl. GQA/MQA and non-causal ring."""
+    run_distributed(_all_batch_cases, world)
 
 
 def test_batch_bf16_dtype_roundtrip():
@@ -140,13 +149,20 @@ def _varlen_case(rank, world, scheme, causal, packing, hq, hkv):
     torch.testing.assert_close(gv, shard(vr.grad, cu, rank, world), **TOL)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("scheme,causal,packing,hq,hkv", [
+VARLEN_CASES = [
     ("ring", True, "qkv", 4, 4), ("ring", False, "kv", 4, 2), ("ring", True, "none", 2, 1),
     ("zigzag", True, "qkv", 4, 4), ("zigzag", True, "kv", 4, 2), ("zigzag", True, "none", 2, 2),
-])
-def test_varlen_schemes(world, scheme, causal, packing, hq, hkv):
-    run_distributed(_varlen_case, world, scheme, causal, packing, hq, hkv)
+]
+
+
+def _all_varlen_cases(rank, world):
+    for scheme, causal, packing, hq, hkv in VARLEN_CASES:
+        _varlen_case(rank, world, scheme, causal, packing, hq, hkv)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_varlen_schemes(world):
+    run_distributed(_all_varlen_cases, world)
 
 
 def _llama3_case(rank, world, causal, packing, hq, hkv, stride):
@@ -191,12 +207,17 @@ def _llama3_case(rank, world, causal, packing, hq, hkv, stride):
     torch.testing.assert_close(gv, sh(vr.grad), **TOL)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("causal,packing,hq,hkv,stride", [
-    (True, "qkv", 4, 4, 1), (True, "kv", 4, 2, 2), (False, "none", 4, 2, 1), (True, "none", 8, 4, 4),
-])
-def test_llama3(world, causal, packing, hq, hkv, stride):
-    run_distributed(_llama3_case, world, causal, packing, hq, hkv, stride)
+LLAMA3_CASES = [(True, "qkv", 4, 4, 1), (True, "kv", 4, 2, 2), (False, "none", 4, 2, 1), (True, "none", 8, 4, 4)]
+
+
+def _all_llama3_cases(rank, world):
+    for causal, packing, hq, hkv, stride in LLAMA3_CASES:
+        _llama3_case(rank, world, causal, packing, hq, hkv, stride)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_llama3(world):
+    run_distributed(_all_llama3_cases, world)
 
 
 def _single_process_case():
