@@ -67,6 +67,28 @@ except AttributeError:  # pragma: no cover - very old torch
     pass
 
 
+def _maybe_dequant(q, k, v, descale):
+    """fp8 extension (utils/fp8.py): ``descale`` is a tensor for a packed input or a (q, k, v) tuple."""
+    from ..utils import fp8
+
+    if not (fp8.is_fp8(q) or fp8.is_fp8(k) or fp8.is_fp8(v)):
+        return q, k, v
+    if descale is None:
+        raise ValueError("fp8 q/k/v need descale=(q_descale, k_descale, v_descale)")
+    dq, dk, dv = descale if isinstance(descale, (tuple, list)) else (descale, descale, descale)
+    return fp8.dequantize(q, dq), fp8.dequantize(k, dk), fp8.dequantize(v, dv)
+
+
+def _split_descale(descale, pack_dim: int, n: int):
+    """descale of a packed (kv / qkv) tensor -> per-tensor descales.  A tensor that carries the pack dimension
+    (size n) is sliced like the data, anything else (None, a scalar tensor, per-head scales, ...) is shared."""
+    if descale is None or isinstance(descale, (tuple, list)):
+        return descale
+    if isinstance(descale, torch.Tensor) and descale.dim() > pack_dim and descale.shape[pack_dim] == n:
+        return tuple(descale.select(pack_dim, i) for i in range(n))
+    return tuple(descale for _ in range(n))
+
+
 def _check_common(q, dropout_p, window_size, alibi_slopes):
     if alibi_slopes is not None:
         raise NotImplementedError("alibi_slopes is not supported (same as the reference)")
@@ -133,8 +155,9 @@ def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=Non
 
 
 def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
-               deterministic, return_attn_probs, group):
+               deterministic, return_attn_probs, group, descale=None):
     _check_common(q, dropout_p, window_size, alibi_slopes)
+    q, k, v = _maybe_dequant(q, k, v, descale)
     if scheme in ("zigzag", "stripe") and not causal:
         raise AssertionError(f"{scheme} attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
@@ -151,8 +174,9 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
 
 
 def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scale, causal, window_size,
-                alibi_slopes, deterministic, return_attn_probs, group):
+                alibi_slopes, deterministic, return_attn_probs, group, descale=None):
     _check_common(q, dropout_p, window_size, alibi_slopes)
+    q, k, v = _maybe_dequant(q, k, v, descale)
     if scheme == "zigzag" and not causal:
         raise AssertionError("zigzag attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
@@ -171,19 +195,26 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
 
 def _define_batch(scheme, prefix):
     def func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
-             alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None):
+             alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, *, descale=None):
         return _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
-                          deterministic, return_attn_probs, group)
+                          deterministic, return_attn_probs, group, descale)
 
     def kvpacked_func(q, kv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
-                      alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None):
+                      alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, *,
+                      descale=None):
+        if descale is not None:  # (q_descale, kv_descale)
+            dq, dkv = descale
+            dk, dv = _split_descale(dkv, 2, 2)
+            descale = (dq, dk, dv)
         return _run_batch(scheme, q, kv[:, :, 0], kv[:, :, 1], dropout_p, softmax_scale, causal,
-                          window_size, alibi_slopes, deterministic, return_attn_probs, group)
+                          window_size, alibi_slopes, deterministic, return_attn_probs, group, descale)
 
     def qkvpacked_func(qkv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
-                       alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None):
+                       alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, *,
+                       descale=None):
         return _run_batch(scheme, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dropout_p, softmax_scale,
-                          causal, window_size, alibi_slopes, deterministic, return_attn_probs, group)
+                          causal, window_size, alibi_slopes, deterministic, return_attn_probs, group,
+                          _split_descale(descale, 2, 3))
 
     doc = ("{name}: q (B, S_local, Hq, D), k/v (B, S_local, Hkv, D) [kv (B,S_local,2,Hkv,D); "
            "qkv (B,S_local,3,H,D)] sharded with the '" + scheme + "' layout over `group`.  Returns out "
@@ -208,22 +239,26 @@ stripe_flash_attn_func, stripe_flash_attn_kvpacked_func, stripe_flash_attn_qkvpa
 def _define_varlen(scheme, prefix):
     def func(q, k, v, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False,
              window_size=(-1, -1), alibi_slopes=None, deterministic=False, return_attn_probs=False,
-             group=None):
+             group=None, *, descale=None):
         return _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scale, causal,
-                           window_size, alibi_slopes, deterministic, return_attn_probs, group)
+                           window_size, alibi_slopes, deterministic, return_attn_probs, group, descale)
 
     def kvpacked_func(q, kv, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False,
                       window_size=(-1, -1), alibi_slopes=None, deterministic=False,
-                      return_attn_probs=False, group=None):
+                      return_attn_probs=False, group=None, *, descale=None):
+        if descale is not None:
+            dq, dkv = descale
+            dk, dv = _split_descale(dkv, 1, 2)
+            descale = (dq, dk, dv)
         return _run_varlen(scheme, q, kv[:, 0], kv[:, 1], cu_seqlens, max_seqlen, dropout_p, softmax_scale,
-                           causal, window_size, alibi_slopes, deterministic, return_attn_probs, group)
+                           causal, window_size, alibi_slopes, deterministic, return_attn_probs, group, descale)
 
     def qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False,
                        window_size=(-1, -1), alibi_slopes=None, deterministic=False,
-                       return_attn_probs=False, group=None):
+                       return_attn_probs=False, group=None, *, descale=None):
         return _run_varlen(scheme, qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens, max_seqlen, dropout_p,
                            softmax_scale, causal, window_size, alibi_slopes, deterministic,
-                           return_attn_probs, group)
+                           return_attn_probs, group, _split_descale(descale, 1, 3))
 
     doc = ("{name}: packed q (T_local, Hq, D), k/v (T_local, Hkv, D) with ONE local cu_seqlens "
            "(global cu_seqlens // world_size); every document is sharded with the '" + scheme +
@@ -290,10 +325,11 @@ def _llama3_peer_plan(global_cu, causal, rank, world, tokens):
 def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
                                   heads_k_stride, local_k_slice, dropout_p=0.0, softmax_scale=None,
                                   causal=False, window_size=(-1, -1), alibi_slopes=None,
-                                  deterministic=False, return_attn_probs=False, group=None):
+                                  deterministic=False, return_attn_probs=False, group=None, *, descale=None):
     """llama3-style CP: q/k/v (T_local, H*, D) are a contiguous slice of the flat token stream; the
     cu_seqlens / local_k_slice come from :func:`llama3_flash_attn_prepare_cu_seqlens`."""
     _check_common(q, dropout_p, window_size, alibi_slopes)
+    q, k, v = _maybe_dequant(q, k, v, descale)
     rank, world = group_info(group)
     k_start = local_k_slice.start or 0
     cu_q_host, cu_k_host = cu_seqlens_to_host(cu_seqlens_q), cu_seqlens_to_host(cu_seqlens_k)
@@ -317,20 +353,26 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
 def llama3_flash_attn_varlen_kvpacked_func(q, kv, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
                                            heads_k_stride, local_k_slice, dropout_p=0.0, softmax_scale=None,
                                            causal=False, window_size=(-1, -1), alibi_slopes=None,
-                                           deterministic=False, return_attn_probs=False, group=None):
+                                           deterministic=False, return_attn_probs=False, group=None, *,
+                                           descale=None):
     """kv (T_local, 2, Hkv, D) variant of :func:`llama3_flash_attn_varlen_func`."""
+    if descale is not None:
+        dq, dkv = descale
+        dk, dv = _split_descale(dkv, 1, 2)
+        descale = (dq, dk, dv)
     return llama3_flash_attn_varlen_func(q, kv[:, 0], kv[:, 1], cu_seqlens_q, cu_seqlens_k, max_seqlen_q,
                                          max_seqlen_k, heads_k_stride, local_k_slice, dropout_p, softmax_scale,
                                          causal, window_size, alibi_slopes, deterministic, return_attn_probs,
-                                         group)
+                                         group, descale=descale)
 
 
 def llama3_flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
                                             heads_k_stride, local_k_slice, dropout_p=0.0, softmax_scale=None,
                                             causal=False, window_size=(-1, -1), alibi_slopes=None,
-                                            deterministic=False, return_attn_probs=False, group=None):
+                                            deterministic=False, return_attn_probs=False, group=None, *,
+                                            descale=None):
     """qkv (T_local, 3, H, D) variant of :func:`llama3_flash_attn_varlen_func`."""
     return llama3_flash_attn_varlen_func(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens_q, cu_seqlens_k,
                                          max_seqlen_q, max_seqlen_k, heads_k_stride, local_k_slice, dropout_p,
                                          softmax_scale, causal, window_size, alibi_slopes, deterministic,
-                                         return_attn_probs, group)
+                                         return_attn_probs, group, descale=_split_descale(descale, 1, 3))

@@ -1,0 +1,66 @@
+"""Block-scaled fp8 inputs (extension, utils/fp8.py): quantise -> attention == attention on the dequantised values."""
+import pytest
+import torch
+
+import ring_flash_attn_b200 as rfa
+from ring_flash_attn_b200.ops.dense import attention_oracle
+from ring_flash_attn_b200.parallel import layouts
+from ring_flash_attn_b200.utils import fp8
+from dist_utils import run_distributed
+
+pytestmark = pytest.mark.skipif(not fp8.FP8_DTYPES, reason="this torch build has no float8 dtypes")
+
+
+def test_quantize_dequantize_roundtrip_and_layouts():
+    torch.manual_seed(0)
+    x = torch.randn(2, 64, 3, 4, 32)
+    for block in [(0, 0, 0, 0, 0), (1, 16, 1, 1, 0), (1, 1, 1, 1, 32), (1, 64, 3, 1, 0)]:
+        q, d = fp8.quantize_blockwise(x, block)
+        assert q.dtype == torch.float8_e4m3fn
+        back = fp8.dequantize(q, d, torch.float32)
+        assert (back - x).abs().max() < 0.07 * x.abs().max()
+    with pytest.raises(ValueError):
+        fp8.dequantize(q, None)
+    with pytest.raises(ValueError):
+        fp8.dequantize(q, torch.ones(2, 5, 1, 1, 1))
+
+
+def _stripe_case(rank, world):
+    # BASELINE.json config 5 in miniature: stripe qkvpacked, fp8 with one scale per (16-token block, head)
+    torch.manual_seed(0)
+    b, s, h, d = 2, 32 * world, 4, 16
+    qkv = torch.randn(b, s, 3, h, d)
+    import torch.distributed as dist
+
+    dist.broadcast(qkv, src=0)
+    local = layouts.shard_stripe(qkv, rank, world)
+    q8, descale = fp8.quantize_blockwise(local, (1, 16, 1, 1, 0))
+    out = rfa.stripe_flash_attn_qkvpacked_func(q8, causal=True, descale=descale)
+    # oracle on the dequantised values of EVERY rank (what the other ranks contribute is their fp8 data too)
+    shards = []
+    for r in range(world):
+        lr = layouts.shard_stripe(qkv, r, world)
+        qr, dr = fp8.quantize_blockwise(lr, (1, 16, 1, 1, 0))
+        shards.append(fp8.dequantize(qr, dr, torch.float32))
+    full = layouts.unshard("stripe", shards, dim=1)
+    ref, _ = attention_oracle(full[:, :, 0].bfloat16(), full[:, :, 1].bfloat16(), full[:, :, 2].bfloat16(), True)
+    torch.testing.assert_close(out.float(), layouts.shard_stripe(ref, rank, world), atol=3e-2, rtol=3e-2)
+    assert out.dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_stripe_fp8_blockscaled(world):
+    run_distributed(_stripe_case, world)
+
+
+def test_kvpacked_and_unpacked_fp8_share_semantics():
+    torch.manual_seed(1)
+    q = torch.randn(1, 32, 4, 16)
+    kv = torch.randn(1, 32, 2, 2, 16)
+    q8, dq = fp8.quantize_blockwise(q, (1, 8, 1, 0))
+    kv8, dkv = fp8.quantize_blockwise(kv, (1, 8, 1, 1, 0))
+    a = rfa.ring_flash_attn_kvpacked_func(q8, kv8, causal=True, descale=(dq, dkv))
+    b = rfa.ring_flash_attn_func(q8, kv8[:, :, 0], kv8[:, :, 1], causal=True, descale=(dq, dkv[:, :, 0], dkv[:, :, 1]))
+    torch.testing.assert_close(a, b)
+    with pytest.raises(ValueError):
+        rfa.ring_flash_attn_kvpacked_func(q8, kv8, causal=True)
