@@ -57,8 +57,12 @@ def _ring_core(query_states, key_states, value_states, *, is_causal, dropout, so
         raise AssertionError("varlen data should be processed in advance (batch size must be 1).")
     if not DATA_PARAMS:
         raise RuntimeError("call update_ring_flash_attn_params(cu_seqlens, group) before the model forward")
+    window = (-1, -1)
     if sliding_window is not None and DATA_PARAMS["max_seqlen_k"] > sliding_window:
-        raise NotImplementedError("sliding-window attention is not supported by context-parallel attention")
+        # transformers' convention (modeling_flash_attention_utils.py: window_size = (w - 1, w - 1)): a token
+        # sees itself and the w - 1 tokens before it.  The window is applied to global positions in the
+        # document, whichever rank holds the keys.
+        window = (int(sliding_window) - 1, 0)
     if deterministic is None:
         deterministic = os.environ.get("FLASH_ATTENTION_DETERMINISTIC", "0") == "1"
     out = llama3_flash_attn_varlen_func(
@@ -66,7 +70,8 @@ def _ring_core(query_states, key_states, value_states, *, is_causal, dropout, so
         cu_seqlens_q=DATA_PARAMS["cu_seqlens_q"], cu_seqlens_k=DATA_PARAMS["cu_seqlens_k"],
         max_seqlen_q=DATA_PARAMS["max_seqlen_q"], max_seqlen_k=DATA_PARAMS["max_seqlen_k"],
         heads_k_stride=heads_k_stride, local_k_slice=DATA_PARAMS["local_k_slice"], dropout_p=dropout,
-        softmax_scale=softmax_scale, causal=True, deterministic=deterministic, group=process_group)
+        softmax_scale=softmax_scale, causal=True, window_size=window, deterministic=deterministic,
+        group=process_group)
     return out.unsqueeze(0)
 
 

@@ -27,13 +27,20 @@ def _expand_kv(x: torch.Tensor, n_rep: int) -> torch.Tensor:
     return x if n_rep == 1 else x.repeat_interleave(n_rep, dim=1)
 
 
-def diag_mask(tq: int, tk: int, diag: Optional[int], device) -> Optional[torch.Tensor]:
-    """Boolean (tq, tk) mask, True = visible; None when everything is visible."""
-    if diag is None or diag >= tk - 1:
+def diag_mask(tq: int, tk: int, diag: Optional[int], device, lo: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Boolean (tq, tk) mask, True = visible (``i + lo <= j <= i + diag``); None when everything is visible."""
+    hi_free = diag is None or diag >= tk - 1
+    lo_free = lo is None or lo + (tq - 1) <= 0
+    if hi_free and lo_free:
         return None
     i = torch.arange(tq, device=device).unsqueeze(1)
     j = torch.arange(tk, device=device).unsqueeze(0)
-    return j <= i + diag
+    m = torch.ones(tq, tk, dtype=torch.bool, device=device)
+    if not hi_free:
+        m &= j <= i + diag
+    if not lo_free:
+        m &= j >= i + lo
+    return m
 
 
 def block_fwd(
@@ -42,6 +49,7 @@ def block_fwd(
     v: torch.Tensor,
     scale: float,
     diag: Optional[int] = None,
+    lo: Optional[int] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """One (query chunk x key segment) block.  Returns (out fp32 (Tq,Hq,D), lse fp32 (Hq,Tq)).
 
@@ -55,7 +63,7 @@ def block_fwd(
     kf = _expand_kv(k.float(), n_rep).transpose(0, 1)
     vf = _expand_kv(v.float(), n_rep).transpose(0, 1)
     s = torch.matmul(qf, kf.transpose(1, 2)) * scale  # (Hq, Tq, Tk)
-    m = diag_mask(tq, tk, diag, q.device)
+    m = diag_mask(tq, tk, diag, q.device, lo)
     if m is not None:
         s = s.masked_fill(~m, NEG_INF)
     lse = torch.logsumexp(s, dim=-1)  # (Hq, Tq); -inf for empty rows
@@ -75,6 +83,7 @@ def block_bwd(
     delta: torch.Tensor,
     scale: float,
     diag: Optional[int] = None,
+    lo: Optional[int] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Gradient contribution of one block given the *global* lse and delta = rowsum(dout * out).
 
@@ -93,7 +102,7 @@ def block_bwd(
     s = torch.matmul(qf, kf.transpose(1, 2)) * scale
     lse_safe = torch.where(torch.isinf(lse), torch.zeros_like(lse), lse)
     p = torch.exp(s - lse_safe.unsqueeze(-1))
-    m = diag_mask(tq, tk, diag, q.device)
+    m = diag_mask(tq, tk, diag, q.device, lo)
     if m is not None:
         p = p.masked_fill(~m, 0.0)
     dv = torch.matmul(p.transpose(1, 2), dof)  # (Hq, Tk, D)
@@ -118,6 +127,7 @@ def attention_oracle(
     v: torch.Tensor,
     causal: bool,
     softmax_scale: Optional[float] = None,
+    window_size: Tuple[int, int] = (-1, -1),
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Dense fp32 attention for batch layout.  q (B,S,Hq,D), k/v (B,S,Hkv,D).
 
@@ -130,11 +140,19 @@ def attention_oracle(
     kf = k.float().repeat_interleave(n_rep, dim=2).permute(0, 2, 1, 3)
     vf = v.float().repeat_interleave(n_rep, dim=2).permute(0, 2, 1, 3)
     sc = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    left, right = window_size
     if causal:
+        right = 0
+    if right >= 0 or left >= 0:
         sk = k.shape[1]
-        i = torch.arange(s, device=q.device).unsqueeze(1)
+        i = torch.arange(s, device=q.device).unsqueeze(1) + (sk - s)  # bottom-right aligned positions
         j = torch.arange(sk, device=q.device).unsqueeze(0)
-        sc = sc.masked_fill(~(j <= i + (sk - s)), NEG_INF)
+        vis = torch.ones(s, sk, dtype=torch.bool, device=q.device)
+        if right >= 0:
+            vis &= j <= i + right
+        if left >= 0:
+            vis &= j >= i - left
+        sc = sc.masked_fill(~vis, NEG_INF)
     lse = torch.logsumexp(sc, dim=-1)
     p = torch.softmax(sc, dim=-1)
     out = torch.matmul(p, vf).permute(0, 2, 1, 3).contiguous()
@@ -148,6 +166,7 @@ def varlen_attention_oracle(
     cu_seqlens: torch.Tensor,
     causal: bool,
     softmax_scale: Optional[float] = None,
+    window_size: Tuple[int, int] = (-1, -1),
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Dense fp32 attention over packed documents.  q (T,Hq,D), k/v (T,Hkv,D), one shared cu_seqlens.
 
@@ -155,7 +174,7 @@ def varlen_attention_oracle(
     outs, lses = [], []
     cu = [int(x) for x in cu_seqlens.tolist()]
     for a, b in zip(cu[:-1], cu[1:]):
-        o, l = attention_oracle(q[None, a:b], k[None, a:b], v[None, a:b], causal, softmax_scale)
+        o, l = attention_oracle(q[None, a:b], k[None, a:b], v[None, a:b], causal, softmax_scale, window_size)
         outs.append(o[0])
         lses.append(l[0])
     return torch.cat(outs, dim=0), torch.cat(lses, dim=-1)

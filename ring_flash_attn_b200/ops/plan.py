@@ -35,7 +35,8 @@ class Segment:
     src: int  # source rank (within the CP group) that owns the keys
     kv_row0: int  # first row inside the source rank's local K/V
     kv_len: int
-    diag: Optional[int]  # None = fully visible; else key j visible to query i iff j <= i + diag
+    diag: Optional[int]  # None = no upper bound; else key j visible to query i only if j <= i + diag
+    lo: Optional[int] = None  # sliding window: key j visible only if j >= i + lo (None = no lower bound)
 
 
 @dataclass
@@ -65,12 +66,16 @@ class CPPlan:
         total = 0
         for s in self.segments:
             n = self.q_chunks[s.chunk].rows
-            total += visible_area(n, s.kv_len, s.diag)
+            total += visible_area(n, s.kv_len, s.diag, s.lo)
         return 4 * total * heads_q * head_dim
 
 
-def visible_area(q_len: int, kv_len: int, diag: Optional[int]) -> int:
-    """Number of (query, key) pairs with ``j <= i + diag`` in a q_len x kv_len block."""
+def visible_area(q_len: int, kv_len: int, diag: Optional[int], lo: Optional[int] = None) -> int:
+    """Number of (query, key) pairs with ``i + lo <= j <= i + diag`` in a q_len x kv_len block."""
+    if lo is not None:
+        # pairs below the lower bound are those with j <= i + lo - 1
+        below = visible_area(q_len, kv_len, lo - 1)
+        return visible_area(q_len, kv_len, diag) - (below if diag is None else min(below, visible_area(q_len, kv_len, diag)))
     if diag is None:
         return q_len * kv_len
     lo = max(0, -diag)  # first row that sees at least one key
@@ -84,39 +89,54 @@ def visible_area(q_len: int, kv_len: int, diag: Optional[int]) -> int:
     return area
 
 
-def _classify(q_pos0: int, q_len: int, k_pos0: int, k_len: int, causal: bool, stride: int = 1,
-              q_phase: int = 0, k_phase: int = 0):
-    """Visibility of a key run against a query run.  Returns "skip", None (full) or an int diag.
+def _ceil_div(a: int, b: int) -> int:
+    return -((-a) // b)
 
-    Positions are ``pos0 + idx * stride + phase``.  stride > 1 is the striped layout."""
-    if not causal:
-        return None
-    if stride == 1:
-        diag = q_pos0 - k_pos0
-    else:
-        # j*W + rk <= i*W + rq  <=>  j <= i + floor((rq - rk) / W) + (q_pos0 - k_pos0)
-        diag = (q_pos0 - k_pos0) + (0 if k_phase <= q_phase else -1)
-    if diag + (q_len - 1) < 0:
+
+def _classify(q_pos0: int, q_len: int, k_pos0: int, k_len: int, causal: bool, stride: int = 1,
+              q_phase: int = 0, k_phase: int = 0, window: Tuple[int, int] = (-1, -1)):
+    """Visibility of a key run against a query run: "skip", or (lo, hi) index offsets with None = unbounded
+    (key j visible to query i iff i + lo <= j <= i + hi).
+
+    Positions are ``pos0 + idx * stride + phase``; stride > 1 is the striped layout.  ``window`` follows
+    flash-attn: key position p_k is visible to query position p_q iff p_q - left <= p_k <= p_q + right,
+    -1 meaning unbounded; ``causal`` forces right = 0."""
+    left, right = window
+    if causal:
+        right = 0
+    # upper bound: p_k <= p_q + right   <=>   j <= i + floor((dq + right) / stride)
+    d = (q_pos0 - k_pos0) * stride + (q_phase - k_phase)  # p_q - p_k at i == j
+    hi = None if right < 0 else (d + right) // stride
+    # lower bound: p_k >= p_q - left    <=>   j >= i + ceil((d - left) / stride)
+    lo = None if left < 0 else _ceil_div(d - left, stride)
+    if hi is not None and hi + (q_len - 1) < 0:
         return "skip"
-    if diag >= k_len - 1:
-        return None
-    return diag
+    if lo is not None and lo > k_len - 1:
+        return "skip"
+    if hi is not None and lo is not None and lo > hi:
+        return "skip"
+    if hi is not None and hi >= k_len - 1:
+        hi = None
+    if lo is not None and lo + (q_len - 1) <= 0:
+        lo = None
+    return (lo, hi)
 
 
 def _add(plan: CPPlan, chunk: int, src: int, kv_row0: int, kv_len: int, vis) -> None:
     if vis == "skip" or kv_len <= 0:
         return
-    # coalesce with the previous segment when it continues the same key run on the same diagonal
+    lo, hi = vis
+    # coalesce with the previous segment when it continues the same key run on the same diagonals
     if plan.segments:
         p = plan.segments[-1]
-        if p.chunk == chunk and p.src == src and p.kv_row0 + p.kv_len == kv_row0:
-            if p.diag is None and vis is None:
+        if p.chunk == chunk and p.src == src and p.kv_row0 + p.kv_len == kv_row0 and p.lo is None and lo is None:
+            if p.diag is None and hi is None:
                 plan.segments[-1] = Segment(chunk, src, p.kv_row0, p.kv_len + kv_len, None)
                 return
-            if p.diag is not None and vis is not None and vis == p.diag - p.kv_len:
+            if p.diag is not None and hi is not None and hi == p.diag - p.kv_len:
                 plan.segments[-1] = Segment(chunk, src, p.kv_row0, p.kv_len + kv_len, p.diag)
                 return
-    plan.segments.append(Segment(chunk, src, kv_row0, kv_len, vis))
+    plan.segments.append(Segment(chunk, src, kv_row0, kv_len, hi, lo))
 
 
 def _src_order(rank: int, world: int) -> List[int]:
@@ -128,18 +148,19 @@ def _src_order(rank: int, world: int) -> List[int]:
 # batch layouts
 # ----------------------------------------------------------------------------------------------
 
-def plan_ring(rank: int, world: int, batch: int, seqlen_local: int, causal: bool) -> CPPlan:
+def plan_ring(rank: int, world: int, batch: int, seqlen_local: int, causal: bool,
+              window: Tuple[int, int] = (-1, -1)) -> CPPlan:
     L = seqlen_local
     plan = CPPlan(world, rank, batch * L, batch * L)
     for b in range(batch):
         plan.q_chunks.append(QChunk(b * L, L))
     for src in _src_order(rank, world):
         for b in range(batch):
-            _add(plan, b, src, b * L, L, _classify(rank * L, L, src * L, L, causal))
+            _add(plan, b, src, b * L, L, _classify(rank * L, L, src * L, L, causal, window=window))
     return plan
 
 
-def plan_zigzag(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
+def plan_zigzag(rank: int, world: int, batch: int, seqlen_local: int, window: Tuple[int, int] = (-1, -1)) -> CPPlan:
     L = seqlen_local
     if L % 2:
         raise ValueError("zigzag needs an even local sequence length")
@@ -155,11 +176,11 @@ def plan_zigzag(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
             for qi in range(2):
                 for ki in range(2):
                     _add(plan, 2 * b + qi, src, b * L + ki * c, c,
-                         _classify(qpos[qi], c, kpos[ki], c, True))
+                         _classify(qpos[qi], c, kpos[ki], c, True, window=window))
     return plan
 
 
-def plan_stripe(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
+def plan_stripe(rank: int, world: int, batch: int, seqlen_local: int, window: Tuple[int, int] = (-1, -1)) -> CPPlan:
     L = seqlen_local
     plan = CPPlan(world, rank, batch * L, batch * L)
     for b in range(batch):
@@ -167,7 +188,7 @@ def plan_stripe(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
     for src in _src_order(rank, world):
         for b in range(batch):
             _add(plan, b, src, b * L, L,
-                 _classify(0, L, 0, L, True, stride=world, q_phase=rank, k_phase=src))
+                 _classify(0, L, 0, L, True, stride=world, q_phase=rank, k_phase=src, window=window))
     return plan
 
 
@@ -175,7 +196,8 @@ def plan_stripe(rank: int, world: int, batch: int, seqlen_local: int) -> CPPlan:
 # varlen layouts (one shared local cu_seqlens; every document is split evenly over the ranks)
 # ----------------------------------------------------------------------------------------------
 
-def plan_ring_varlen(rank: int, world: int, cu_seqlens: Sequence[int], causal: bool) -> CPPlan:
+def plan_ring_varlen(rank: int, world: int, cu_seqlens: Sequence[int], causal: bool,
+                     window: Tuple[int, int] = (-1, -1)) -> CPPlan:
     cu = [int(x) for x in cu_seqlens]
     total = cu[-1]
     plan = CPPlan(world, rank, total, total)
@@ -184,11 +206,11 @@ def plan_ring_varlen(rank: int, world: int, cu_seqlens: Sequence[int], causal: b
     for src in _src_order(rank, world):
         for d, (a, b) in enumerate(zip(cu[:-1], cu[1:])):
             n = b - a
-            _add(plan, d, src, a, n, _classify(rank * n, n, src * n, n, causal))
+            _add(plan, d, src, a, n, _classify(rank * n, n, src * n, n, causal, window=window))
     return plan
 
 
-def plan_zigzag_varlen(rank: int, world: int, cu_seqlens: Sequence[int]) -> CPPlan:
+def plan_zigzag_varlen(rank: int, world: int, cu_seqlens: Sequence[int], window: Tuple[int, int] = (-1, -1)) -> CPPlan:
     cu = [int(x) for x in cu_seqlens]
     total = cu[-1]
     plan = CPPlan(world, rank, total, total)
@@ -206,7 +228,7 @@ def plan_zigzag_varlen(rank: int, world: int, cu_seqlens: Sequence[int]) -> CPPl
             for qi in range(2):
                 for ki in range(2):
                     _add(plan, 2 * d + qi, src, a + ki * c, c,
-                         _classify(qpos[qi], c, kpos[ki], c, True))
+                         _classify(qpos[qi], c, kpos[ki], c, True, window=window))
     return plan
 
 
@@ -215,7 +237,8 @@ def plan_zigzag_varlen(rank: int, world: int, cu_seqlens: Sequence[int]) -> CPPl
 # ----------------------------------------------------------------------------------------------
 
 def plan_llama3(rank: int, world: int, tokens_local: int, cu_seqlens_q: Sequence[int],
-                cu_seqlens_k: Sequence[int], k_slice_start: int, causal: bool) -> CPPlan:
+                cu_seqlens_k: Sequence[int], k_slice_start: int, causal: bool,
+                window: Tuple[int, int] = (-1, -1)) -> CPPlan:
     """Plan from the outputs of ``llama3_flash_attn_prepare_cu_seqlens``.
 
     ``cu_seqlens_k`` is relative to ``k_slice_start`` in the *global* (gathered) key stream; the
@@ -232,13 +255,21 @@ def plan_llama3(rank: int, world: int, tokens_local: int, cu_seqlens_q: Sequence
         k0 = k_slice_start + cuk[d]
         k1 = k_slice_start + cuk[d + 1]
         kn = k1 - k0
-        base_diag = kn - qn  # bottom-right alignment
+        # position of the chunk's first query inside its document (document key 0 sits at k0).  Causal:
+        # bottom-right alignment as flash-attn defines it (prepare() trims the keys at the last local query,
+        # so both expressions agree); non-causal windows need the true position because the keys run on to
+        # the end of the document
+        base_diag = kn - qn if causal else rank * L + cuq[d] - k0
         for src in range(world):
             lo, hi = max(k0, src * L), min(k1, (src + 1) * L)
             if hi <= lo:
                 continue
             # key j' (within this piece) is doc key j' + (lo - k0)
-            vis = _classify(base_diag, qn, lo - k0, hi - lo, causal) if causal else None
+            if causal or window != (-1, -1):
+                # query i of the chunk sits at document key position i + base_diag
+                vis = _classify(base_diag, qn, lo - k0, hi - lo, causal, window=window)
+            else:
+                vis = (None, None)
             pieces.append((src, d, lo - src * L, hi - lo, vis))
     for src in _src_order(rank, world):
         for (s, d, r0, n, vis) in pieces:

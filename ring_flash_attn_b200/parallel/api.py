@@ -13,6 +13,7 @@ torch.distributed fallback.
 from __future__ import annotations
 
 import functools
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -57,7 +58,37 @@ class CPAttention(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None, None, None
 
 
+KERNEL_HEAD_DIM = 128  # the sm_100a kernels are specialised for this head size
+
+
+def _pad_head_dim(q) -> int:
+    """Columns of zero padding that bring the head size to the kernels' 128.
+
+    Zero columns change neither Q.K^T nor the first ``d`` columns of P.V, and their gradients are exactly zero,
+    so a head size below 128 runs on the tcgen05 kernels (at the cost of the padded FLOPs) instead of dropping
+    to the dense torch blocks.  ``RFA_B200_PAD_HEAD_DIM=0`` disables it, ``=force`` applies it on any device
+    (used by the CPU tests)."""
+    mode = os.environ.get("RFA_B200_PAD_HEAD_DIM", "1")
+    d = q.shape[-1]
+    if mode == "0" or d >= KERNEL_HEAD_DIM:
+        return 0
+    if mode == "force":
+        return KERNEL_HEAD_DIM - d
+    if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16):
+        from ..ops import cuda_ext
+
+        if cuda_ext.available_for(q):
+            return KERNEL_HEAD_DIM - d
+    return 0
+
+
 def _cp_apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic):
+    pad = _pad_head_dim(q)
+    if pad:
+        d = q.shape[-1]
+        q, k, v = (torch.nn.functional.pad(t, (0, pad)) for t in (q, k, v))
+        out, lse = CPAttention.apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic)
+        return out[..., :d].contiguous(), lse
     return CPAttention.apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic)
 
 
@@ -94,8 +125,8 @@ def _check_common(q, dropout_p, window_size, alibi_slopes):
         raise NotImplementedError("alibi_slopes is not supported (same as the reference)")
     if dropout_p != 0.0:
         raise NotImplementedError("dropout_p > 0 is not supported by context-parallel attention")
-    if tuple(window_size) != (-1, -1):
-        raise NotImplementedError("window_size (sliding window) is not supported across shards")
+    if len(tuple(window_size)) != 2:
+        raise ValueError("window_size must be (left, right)")
 
 
 def _scale(q, softmax_scale):
@@ -127,31 +158,36 @@ def cu_seqlens_to_host(cu: torch.Tensor) -> Tuple[int, ...]:
     return vals
 
 
+def _window(window_size) -> Tuple[int, int]:
+    left, right = (int(x) for x in window_size)
+    return (-1 if left < 0 else left, -1 if right < 0 else right)
+
+
 @functools.lru_cache(maxsize=512)
-def _batch_plan(scheme, rank, world, batch, seqlen, causal):
+def _batch_plan(scheme, rank, world, batch, seqlen, causal, window=(-1, -1)):
     if scheme == "ring":
-        return P.plan_ring(rank, world, batch, seqlen, causal)
+        return P.plan_ring(rank, world, batch, seqlen, causal, window)
     if scheme == "zigzag":
-        return P.plan_zigzag(rank, world, batch, seqlen)
+        return P.plan_zigzag(rank, world, batch, seqlen, window)
     if scheme == "stripe":
-        return P.plan_stripe(rank, world, batch, seqlen)
+        return P.plan_stripe(rank, world, batch, seqlen, window)
     raise ValueError(scheme)
 
 
 @functools.lru_cache(maxsize=512)
-def _varlen_plan(scheme, rank, world, cu, causal):
+def _varlen_plan(scheme, rank, world, cu, causal, window=(-1, -1)):
     if scheme == "ring":
-        return P.plan_ring_varlen(rank, world, cu, causal)
+        return P.plan_ring_varlen(rank, world, cu, causal, window)
     if scheme == "zigzag":
-        return P.plan_zigzag_varlen(rank, world, cu)
+        return P.plan_zigzag_varlen(rank, world, cu, window)
     raise ValueError(scheme)
 
 
 @functools.lru_cache(maxsize=512)
-def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=None):
+def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=None, window=(-1, -1)):
     # global_cu is part of the cache key on purpose: plans with equal local content but different global
     # layouts must not share their per-plan caches (peers' needs, push tables)
-    return P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal)
+    return P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal, window)
 
 
 def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
@@ -162,8 +198,9 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
         raise AssertionError(f"{scheme} attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
     b, s, hq, d = q.shape
-    plan = _batch_plan(scheme, rank, world, b, s, bool(causal))
-    plan.peer = lambda r, _a=(scheme, world, b, s, bool(causal)): _batch_plan(_a[0], r, *_a[1:])
+    win = _window(window_size)
+    plan = _batch_plan(scheme, rank, world, b, s, bool(causal), win)
+    plan.peer = lambda r, _a=(scheme, world, b, s, bool(causal), win): _batch_plan(_a[0], r, *_a[1:])
     out, lse = _cp_apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
                                  v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
                                  "ring", 1, deterministic)
@@ -181,8 +218,9 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
         raise AssertionError("zigzag attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
     cu_host = cu_seqlens_to_host(cu_seqlens)
-    plan = _varlen_plan(scheme, rank, world, cu_host, bool(causal))
-    plan.peer = lambda r, _a=(scheme, world, cu_host, bool(causal)): _varlen_plan(_a[0], r, *_a[1:])
+    win = _window(window_size)
+    plan = _varlen_plan(scheme, rank, world, cu_host, bool(causal), win)
+    plan.peer = lambda r, _a=(scheme, world, cu_host, bool(causal), win): _varlen_plan(_a[0], r, *_a[1:])
     if plan.q_rows != q.shape[0]:
         raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
     out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic)
@@ -338,7 +376,8 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
     if hit is not None and hit is getattr(cu_seqlens_k, "_rfa_llama3", None) and \
             hit[1:] == (cu_q_host, cu_k_host, rank, world, bool(causal)):
         glob = hit[0]
-    plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal), glob)
+    plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal), glob,
+                        _window(window_size))
     if glob is not None:
         plan.peer = lambda r, _g=glob, _w=world, _c=bool(causal), _t=q.shape[0]: _llama3_peer_plan(_g, _c, r, _w, _t)
     elif world > 1:

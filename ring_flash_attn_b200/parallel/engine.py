@@ -44,11 +44,21 @@ def _use_cuda_kernels(q: torch.Tensor, k: Optional[torch.Tensor] = None) -> bool
     return attn_cuda.supported(q, q if k is None else k)
 
 
+def plan_has_window(plan: CPPlan) -> bool:
+    """Sliding-window plans carry a lower bound per segment; the sm_100a kernels do not implement it yet, so
+    such calls run the dense torch blocks (on whatever device the tensors live)."""
+    cached = getattr(plan, "_has_window", None)
+    if cached is None:
+        cached = any(s.lo is not None for s in plan.segments)
+        plan._has_window = cached
+    return cached
+
+
 def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out, lse):
     """Fold the contribution of one source shard into the running (out, lse)."""
     if not segs:
         return out, lse
-    if _use_cuda_kernels(q, k_src):
+    if _use_cuda_kernels(q, k_src) and not plan_has_window(plan):
         from ..ops import attn_cuda
 
         p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
@@ -60,7 +70,7 @@ def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out,
         ch = plan.q_chunks[s.chunk]
         rows = slice(ch.row0, ch.row0 + ch.rows)
         kv = slice(s.kv_row0, s.kv_row0 + s.kv_len)
-        b_out, b_lse = dense.block_fwd(q[rows], k_src[kv], v_src[kv], scale, s.diag)
+        b_out, b_lse = dense.block_fwd(q[rows], k_src[kv], v_src[kv], scale, s.diag, s.lo)
         merge_partial(out, lse, b_out, b_lse, rows)
     return out, lse
 
@@ -72,7 +82,7 @@ def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse,
     dv = torch.zeros(v_src.shape, dtype=torch.float32, device=q.device)
     if not segs:
         return dk, dv
-    if _use_cuda_kernels(q, k_src):
+    if _use_cuda_kernels(q, k_src) and not plan_has_window(plan):
         from ..ops import attn_cuda
 
         attn_cuda.segments_backward(plan, segs, dout, q, k_src, v_src, lse, delta, scale, dq, dk, dv,
@@ -83,7 +93,7 @@ def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse,
         rows = slice(ch.row0, ch.row0 + ch.rows)
         kv = slice(s.kv_row0, s.kv_row0 + s.kv_len)
         b_dq, b_dk, b_dv = dense.block_bwd(dout[rows], q[rows], k_src[kv], v_src[kv], lse[:, rows],
-                                           delta[:, rows], scale, s.diag)
+                                           delta[:, rows], scale, s.diag, s.lo)
         dq[rows] += b_dq
         dk[kv] += b_dk
         dv[kv] += b_dv
@@ -240,7 +250,7 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
     if not _use_cuda_kernels(q, k):
         return False
-    if plan is not None and not getattr(plan, "fused_ok", True):
+    if plan is not None and (not getattr(plan, "fused_ok", True) or plan_has_window(plan)):
         return False
     from . import fused
 

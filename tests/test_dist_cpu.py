@@ -21,7 +21,7 @@ def _bcast(t):
     return t
 
 
-def _batch_case(rank, world, scheme, causal, packing, hq, hkv, dtype):
+def _batch_case(rank, world, scheme, causal, packing, hq, hkv, dtype, window=(-1, -1)):
     torch.manual_seed(0)
     b, d = 2, 16
     s = 8 * world * 2
@@ -31,7 +31,7 @@ def _batch_case(rank, world, scheme, causal, packing, hq, hkv, dtype):
     dout = _bcast(torch.randn(b, s, hq, d, dtype=dtype))
     shard = getattr(layouts, f"shard_{scheme}")
     qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
-    ref_out, ref_lse = attention_oracle(qr, kr, vr, causal)
+    ref_out, ref_lse = attention_oracle(qr, kr, vr, causal, window_size=window)
     ref_out.backward(dout.float())
 
     lq, lk, lv = (shard(x, rank, world).detach().requires_grad_(True) for x in (q, k, v))
@@ -39,14 +39,14 @@ def _batch_case(rank, world, scheme, causal, packing, hq, hkv, dtype):
     if packing == "qkv":
         qkv = torch.stack([lq, lk, lv], dim=2).detach().requires_grad_(True)
         fn = getattr(rfa, f"{prefix}_flash_attn_qkvpacked_func")
-        out, lse, _ = fn(qkv, causal=causal, return_attn_probs=True)
+        out, lse, _ = fn(qkv, causal=causal, window_size=window, return_attn_probs=True)
     elif packing == "kv":
         kv = torch.stack([lk, lv], dim=2).detach().requires_grad_(True)
         fn = getattr(rfa, f"{prefix}_flash_attn_kvpacked_func")
-        out, lse, _ = fn(lq, kv, causal=causal, return_attn_probs=True)
+        out, lse, _ = fn(lq, kv, causal=causal, window_size=window, return_attn_probs=True)
     else:
         fn = getattr(rfa, f"{prefix}_flash_attn_func")
-        out, lse, _ = fn(lq, lk, lv, causal=causal, return_attn_probs=True)
+        out, lse, _ = fn(lq, lk, lv, causal=causal, window_size=window, return_attn_probs=True)
     assert out.dtype == dtype and lse.dtype == torch.float32
     out.backward(shard(dout, rank, world))
     if packing == "qkv":
@@ -101,7 +101,7 @@ def _config1(rank, world):
     torch.testing.assert_close(lse, layouts.shard_ring(ref_lse, rank, world, dim=2), atol=1e-4, rtol=1e-4)
 
 
-def _varlen_case(rank, world, scheme, causal, packing, hq, hkv):
+def _varlen_case(rank, world, scheme, causal, packing, hq, hkv, window=(-1, -1)):
     torch.manual_seed(0)
     d = 16
     unit = 2 * world
@@ -116,7 +116,7 @@ def _varlen_case(rank, world, scheme, causal, packing, hq, hkv):
     dout = _bcast(torch.randn(total, hq, d))
     cu_t = torch.tensor(cu, dtype=torch.int32)
     qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
-    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal)
+    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal, window_size=window)
     ref_out.backward(dout)
     shard = layouts.shard_ring_varlen if scheme == "ring" else layouts.shard_zigzag_varlen
     lq, lk, lv = (shard(x, cu, rank, world).detach().requires_grad_(True) for x in (q, k, v))
@@ -126,14 +126,14 @@ def _varlen_case(rank, world, scheme, causal, packing, hq, hkv):
     if packing == "qkv":
         qkv = torch.stack([lq, lk, lv], dim=1).detach().requires_grad_(True)
         out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_varlen_qkvpacked_func")(
-            qkv, local_cu, max_s, causal=causal, return_attn_probs=True)
+            qkv, local_cu, max_s, causal=causal, window_size=window, return_attn_probs=True)
     elif packing == "kv":
         kv = torch.stack([lk, lv], dim=1).detach().requires_grad_(True)
         out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_varlen_kvpacked_func")(
-            lq, kv, local_cu, max_s, causal=causal, return_attn_probs=True)
+            lq, kv, local_cu, max_s, causal=causal, window_size=window, return_attn_probs=True)
     else:
         out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_varlen_func")(
-            lq, lk, lv, local_cu, max_s, causal=causal, return_attn_probs=True)
+            lq, lk, lv, local_cu, max_s, causal=causal, window_size=window, return_attn_probs=True)
     out.backward(shard(dout, cu, rank, world))
     if packing == "qkv":
         gq, gk, gv = qkv.grad[:, 0], qkv.grad[:, 1], qkv.grad[:, 2]
@@ -165,7 +165,7 @@ def test_varlen_schemes(world):
     run_distributed(_all_varlen_cases, world)
 
 
-def _llama3_case(rank, world, causal, packing, hq, hkv, stride):
+def _llama3_case(rank, world, causal, packing, hq, hkv, stride, window=(-1, -1)):
     torch.manual_seed(0)
     d = 8
     cu = [0, 3 * world + 1, 7 * world - 1, 12 * world]
@@ -176,7 +176,7 @@ def _llama3_case(rank, world, causal, packing, hq, hkv, stride):
     dout = _bcast(torch.randn(total, hq, d))
     cu_t = torch.tensor(cu, dtype=torch.int32)
     qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
-    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal)
+    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal, window_size=window)
     ref_out.backward(dout)
     sh = lambda x: layouts.shard_llama3(x, rank, world)  # noqa: E731
     lq, lk, lv = (sh(x).detach().requires_grad_(True) for x in (q, k, v))
@@ -184,15 +184,17 @@ def _llama3_case(rank, world, causal, packing, hq, hkv, stride):
     if packing == "qkv":
         qkv = torch.stack([lq, lk, lv], dim=1).detach().requires_grad_(True)
         out, lse, _ = rfa.llama3_flash_attn_varlen_qkvpacked_func(
-            qkv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal, return_attn_probs=True)
+            qkv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal, window_size=window,
+            return_attn_probs=True)
     elif packing == "kv":
         kv = torch.stack([lk, lv], dim=1).detach().requires_grad_(True)
         out, lse, _ = rfa.llama3_flash_attn_varlen_kvpacked_func(
-            lq, kv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal, return_attn_probs=True)
+            lq, kv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal, window_size=window,
+            return_attn_probs=True)
     else:
         out, lse, _ = rfa.llama3_flash_attn_varlen_func(
             lq, lk, lv, cq, ck, mq, mk, heads_k_stride=stride, local_k_slice=ks, causal=causal,
-            return_attn_probs=True)
+            window_size=window, return_attn_probs=True)
     out.backward(sh(dout))
     if packing == "qkv":
         gq, gk, gv = qkv.grad[:, 0], qkv.grad[:, 1], qkv.grad[:, 2]
@@ -220,6 +222,29 @@ def test_llama3(world):
     run_distributed(_all_llama3_cases, world)
 
 
+def _all_window_cases(rank, world):
+    """Sliding window (left, right) applied to *global* positions, every scheme, windows smaller and larger
+    than a shard (the reference forwards window_size to each per-block flash_attn call, which is only
+    meaningful for its llama3 path: /root/reference/ring_flash_attn/llama3_flash_attn_varlen.py:147)."""
+    for win in ((5, 0), (8 * world + 3, 0)):
+        _batch_case(rank, world, "ring", True, "qkv", 4, 4, torch.float32, win)
+        _batch_case(rank, world, "zigzag", True, "kv", 4, 2, torch.float32, win)
+        _batch_case(rank, world, "stripe", True, "none", 2, 1, torch.float32, win)
+        _varlen_case(rank, world, "ring", True, "kv", 4, 2, win)
+        _varlen_case(rank, world, "zigzag", True, "none", 2, 2, win)
+        _llama3_case(rank, world, True, "kv", 4, 2, 2, win)
+    # non-causal two-sided windows (ring and llama3 only: zigzag/stripe are causal-only layouts)
+    for win in ((3, 2), (0, 7), (-1, 4), (6, -1)):
+        _batch_case(rank, world, "ring", False, "none", 2, 2, torch.float32, win)
+        _varlen_case(rank, world, "ring", False, "qkv", 2, 2, win)
+        _llama3_case(rank, world, False, "none", 2, 1, 1, win)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sliding_window(world):
+    run_distributed(_all_window_cases, world)
+
+
 def _single_process_case():
     # world_size 1 without any process group: every scheme degenerates to plain attention
     torch.manual_seed(0)
@@ -228,6 +253,38 @@ def _single_process_case():
     for fn in (rfa.ring_flash_attn_qkvpacked_func, rfa.zigzag_ring_flash_attn_qkvpacked_func,
                rfa.stripe_flash_attn_qkvpacked_func):
         torch.testing.assert_close(fn(qkv, causal=True), ref, **TOL)
+
+
+def _padded_head_dim_cases(rank, world):
+    # d=16 padded to the kernels' 128: identical results, gradients of the padding never leak out
+    _batch_case(rank, world, "zigzag", True, "qkv", 2, 2, torch.float32)
+    _varlen_case(rank, world, "ring", True, "kv", 4, 2)
+    _llama3_case(rank, world, True, "none", 4, 2, 1)
+
+
+def test_head_dim_padding(monkeypatch):
+    monkeypatch.setenv("RFA_B200_PAD_HEAD_DIM", "force")
+    run_distributed(_padded_head_dim_cases, 2)
+
+
+def test_head_dim_padding_reaches_engine(monkeypatch):
+    from ring_flash_attn_b200.parallel import api, engine
+
+    monkeypatch.setenv("RFA_B200_PAD_HEAD_DIM", "force")
+    seen = []
+    real = engine.cp_forward
+    monkeypatch.setattr(engine, "cp_forward", lambda plan, q, *a, **kw: (seen.append(q.shape[-1]), real(plan, q, *a, **kw))[1])
+    qkv = torch.randn(1, 32, 3, 2, 24, requires_grad=True)
+    ref, _ = attention_oracle(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], True)
+    out = rfa.ring_flash_attn_qkvpacked_func(qkv, causal=True)
+    assert seen == [api.KERNEL_HEAD_DIM] and out.shape[-1] == 24 and out.is_contiguous()
+    torch.testing.assert_close(out, ref, **TOL)
+    g, = torch.autograd.grad(out.sum(), qkv)
+    gr, = torch.autograd.grad(ref.sum(), qkv)
+    torch.testing.assert_close(g, gr, **TOL)
+    monkeypatch.setenv("RFA_B200_PAD_HEAD_DIM", "0")
+    rfa.ring_flash_attn_qkvpacked_func(qkv, causal=True)
+    assert seen[-1] == 24
 
 
 def test_single_process_no_group():

@@ -162,3 +162,41 @@ def test_lse_layout_kernels_match_torch():
     ref = lse_layout._unflatten_torch(packed, cu, 267)
     for b, (a, e) in enumerate(zip([0, 5, 133], [5, 133, 400])):
         assert torch.equal(un[b, :, : e - a], ref[b, :, : e - a])
+
+
+def test_world1_sliding_window_on_device():
+    """window_size on a GPU tensor: the plan carries the lower bound and (until the kernels learn it) the
+    dense torch blocks run on the device - results must still match the oracle."""
+    torch.manual_seed(0)
+    q = torch.randn(1, 384, 4, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    kv = torch.randn(1, 384, 2, 2, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(1, 384, 4, 128, device="cuda").to(torch.bfloat16)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    ref_out, _ = attention_oracle(rq, rkv[:, :, 0], rkv[:, :, 1], True, window_size=(100, 0))
+    ref_out.backward(dout.float())
+    out = rfa.zigzag_ring_flash_attn_kvpacked_func(q, kv, causal=True, window_size=(100, 0))
+    out.backward(dout)
+    torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+    assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
+    assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
+
+
+@pytest.mark.parametrize("d", [64, 96])
+def test_world1_small_head_dim_runs_on_kernels(d):
+    """head_dim < 128 is zero-padded to the kernels' head size (parallel/api.py:_pad_head_dim) - still our
+    launches (counter moves), still the oracle's numbers with the caller's 1/sqrt(d) scale."""
+    from ring_flash_attn_b200.ops import cuda_ext
+
+    torch.manual_seed(0)
+    qkv = (torch.randn(1, 512, 3, 4, d, device="cuda") * 0.8).to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(1, 512, 4, d, device="cuda").to(torch.bfloat16)
+    ref = qkv.detach().float().requires_grad_(True)
+    ref_out, _ = attention_oracle(ref[:, :, 0], ref[:, :, 1], ref[:, :, 2], True)
+    ref_out.backward(dout.float())
+    before = cuda_ext.launch_counter().value
+    out = rfa.zigzag_ring_flash_attn_qkvpacked_func(qkv, causal=True)
+    out.backward(dout)
+    assert cuda_ext.launch_counter().value > before
+    assert out.shape == (1, 512, 4, d)
+    torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+    assert (qkv.grad.float() - ref.grad).abs().max().item() < 5e-2 * ref.grad.abs().max().item() + 2e-2

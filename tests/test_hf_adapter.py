@@ -81,6 +81,12 @@ def test_replacement_binds_any_signature_generation():
 
     ref, _ = attention_oracle(q, q, q, True)
     torch.testing.assert_close(out, ref, atol=1e-5, rtol=1e-4)
+    # sliding window: HF semantics = the token itself plus the (w - 1) tokens before it
+    out_w = fn(q, q, q, None, 16, True, 0.0, sliding_window=5)
+    ref_w, _ = attention_oracle(q, q, q, True, window_size=(4, 0))
+    torch.testing.assert_close(out_w, ref_w, atol=1e-5, rtol=1e-4)
+    assert not torch.allclose(out_w, ref)
+    torch.testing.assert_close(fn(q, q, q, None, 16, True, 0.0, sliding_window=16), ref, atol=1e-5, rtol=1e-4)
     with pytest.raises(AssertionError):
         fn(q, q, q, None, 16, False)
     with pytest.raises(AssertionError):
