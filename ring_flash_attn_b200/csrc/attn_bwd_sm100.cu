@@ -51,6 +51,8 @@ constexpr int kQHalf = kQBytes / 2;                // 64-wide swizzled sub-tile 
 constexpr int kKVHalf = kKVBytes / 2;              // 16 KB
 constexpr int kDSBytes = kTileK * kTileQ * 2;      // 16 KB
 constexpr int kDQBytes = kTileQ * kD * 4;          // 32 KB fp32 staging
+constexpr int kBulkPitch = kD * 4 + 16;            // experimental bulk dK/dV epilogue: padded fp32 row
+constexpr int kBulkStageBytes = kTileK * kBulkPitch;  // 66 KB per tile; dK at smem_k, dV right behind it
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 192, kColDV = 256, kColDK = 384;
 
@@ -71,6 +73,7 @@ struct Barriers {
   uint32_t pad;
 };
 
+static_assert(2 * kBulkStageBytes <= 2 * kKVBytes + kStages * 2 * kQBytes, "bulk staging must fit in K|V|Q/dO");
 constexpr int kStatBytes = kStages * 2 * kTileQ * 4;  // lse / delta ring, same slots as Q/dO
 constexpr int kSmemBytes =
     2 * kKVBytes + kStages * 2 * kQBytes + kDSBytes + kDQBytes + kStatBytes + 1024 /*barriers*/ + 1024 /*slack*/;
@@ -479,13 +482,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     const bool bulk = remote && p.dkv.bulk != 0 && total_tiles > 0;
     if (bulk) {
-      // Experimental (RFA_B200_DKV_BULK=1, off by default until validated on hardware): stage the fp32 tile
-      // row-major in shared memory that is idle by now (K|V for dK, the first two Q/dO stages for dV) and let one
-      // thread send each 512-byte row with cp.async.bulk, instead of one 16-byte NVLink store per lane and row.
+      // Experimental (RFA_B200_DKV_BULK=1, off by default until validated on hardware).  The default epilogue
+      // below sends one 16-byte NVLink store per lane and row.  Here every thread (== key row) parks its fp32
+      // row in shared memory that is idle by now (dK: K|V plus the head of the Q/dO ring, dV: the rest of the
+      // Q/dO ring) and ships it itself with one 512-byte cp.async.bulk - no cross-thread hand-off is needed
+      // because a thread only sends what it wrote.  Rows are pitched 528 bytes apart so that the 16-byte stores
+      // of a warp fall into 8 distinct bank groups (4 wavefronts per instruction, the minimum for 512 bytes).
       const int which = half;
-      float* stage = reinterpret_cast<float*>(which == 0 ? smem_k : smem_qdo);
+      uint8_t* stage = which == 0 ? smem_k : smem_k + kBulkStageBytes;
       const uint32_t col = tmem + (which == 0 ? kColDK : kColDV) + lane_addr;
-      float* mine = stage + key * kD;
+      float* mine = reinterpret_cast<float*>(stage + key * kBulkPitch);
 #pragma unroll
       for (int c = 0; c < 128; c += 32) {
         uint32_t r[32];
@@ -496,14 +502,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           *reinterpret_cast<uint4*>(mine + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
       }
       fence_proxy_async_smem();
-      named_bar_sync(1 + half, 128);
-      if (wg_tid == 0) {
+      if (key_ok) {
         float* base = which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner];
-        char* g = reinterpret_cast<char*>(base + (static_cast<size_t>(it.out_row0) * p.hkv + kv_head) * kD);
-        const size_t gstride = static_cast<size_t>(p.hkv) * kD * sizeof(float);
-        for (int rr = 0; rr < it.kv_rows; ++rr) bulk_store(g + rr * gstride, stage + rr * kD, kD * sizeof(float));
+        bulk_store(base + (static_cast<size_t>(row) * p.hkv + kv_head) * kD, mine, kD * sizeof(float));
         tma_store_commit();
-        tma_store_wait<0>();
+        tma_store_wait<0>();  // written, not just read: the flag below must not overtake the data
         fence_proxy_async_all();
       }
     } else {

@@ -13,3 +13,8 @@ for bulk in 0 1; do
   RFA_B200_DKV_BULK=$bulk SWEEP=16,24,32 timeout 600 $TR --master-port 29542 benchmark/multi_breakdown.py > gpurun_out/breakdown_bulk$bulk.log 2>&1
   grep -E "^t[0-9]" gpurun_out/breakdown_bulk$bulk.log | cut -c1-120
 done
+echo "== BASELINE.json configs 2-5 (ours, then the reference), roofline fractions"
+for impl in ours reference; do
+  timeout 900 $TR --master-port 29543 benchmark/bench_configs.py --impl $impl > gpurun_out/bench_configs_${impl}_$N.jsonl 2> gpurun_out/bench_configs_${impl}_$N.err
+  grep '^{' gpurun_out/bench_configs_${impl}_$N.jsonl | cut -c1-260
+done
