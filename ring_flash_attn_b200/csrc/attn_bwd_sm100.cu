@@ -80,7 +80,7 @@ constexpr int kSmemBytes =
 
 // Query tiles of one segment that can see this key tile.
 struct QGeom {
-  int q_row0, q_len, diag;
+  int q_row0, q_len, diag, lo;
   int t_begin, t_end;  // 64-row tile range
 };
 __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
@@ -88,6 +88,7 @@ __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
   g.q_row0 = s.q_row0;
   g.q_len = s.q_len;
   g.diag = s.diag;
+  g.lo = s.lo;
   const int first = s.diag >= 0 ? 0 : -s.diag;  // first chunk row that sees key 0 of the tile
   g.t_begin = first / kTileQ;
   g.t_end = (s.q_len + kTileQ - 1) / kTileQ;
@@ -95,7 +96,7 @@ __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
   return g;
 }
 
-template <typename T>
+template <typename T, bool kWindow>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -413,10 +414,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const long long first_q = static_cast<long long>(key) - g.diag - static_cast<long long>(ti) * kTileQ;
           const int q_lo = !key_ok ? kTileQ : (first_q < 0 ? 0 : (first_q > kTileQ ? kTileQ : static_cast<int>(first_q)));
           float pr[32];
+          if constexpr (kWindow) {
+            // sliding window: ... and iff key >= qi + lo  <=>  qi <= key - lo (the host already dropped the query
+            // tiles past the last such row)
+            const long long last_q = static_cast<long long>(key) - g.lo - static_cast<long long>(ti) * kTileQ;
+            const int q_hi = last_q < 0 ? 0 : (last_q >= kTileQ ? kTileQ : static_cast<int>(last_q) + 1);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float e = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -lse2[c]));
-            pr[c] = (c0 + c) >= q_lo ? e : 0.f;
+            for (int c = 0; c < 32; ++c) {
+              const float e = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -lse2[c]));
+              pr[c] = ((c0 + c) >= q_lo && (c0 + c) < q_hi) ? e : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float e = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -lse2[c]));
+              pr[c] = (c0 + c) >= q_lo ? e : 0.f;
+            }
           }
           {
             uint32_t pk[16];
@@ -651,17 +664,19 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
   if (const char* e = make_plain_tensor_map(&tdq, dq_accum, 4, bwd::kTileQ, bwd::kD)) return e;
   dim3 grid(n_blocks, 1, 1), block(bwd::kThreads, 1, 1);
   cudaError_t err;
+  err = cudaSuccess;
+  auto launch = [&](auto kern) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+    if (err == cudaSuccess) kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
+  };
   if (dtype == kDtypeBF16) {
-    auto kern = bwd::attn_bwd_kernel<__nv_bfloat16>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
-    if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
+    if (p.window) launch(bwd::attn_bwd_kernel<__nv_bfloat16, true>);
+    else launch(bwd::attn_bwd_kernel<__nv_bfloat16, false>);
   } else {
-    auto kern = bwd::attn_bwd_kernel<__half>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
-    if (err != cudaSuccess) return cudaGetErrorString(err);
-    kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
+    if (p.window) launch(bwd::attn_bwd_kernel<__half, true>);
+    else launch(bwd::attn_bwd_kernel<__half, false>);
   }
+  if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

@@ -125,6 +125,7 @@ const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t str
 struct FwdParams {
   const WorkItem* items;
   const KVSegment* segs;
+  const int* seg_lo;  // sliding window only (else nullptr): per segment, key j visible to chunk row i iff j >= i + lo
   void* out;  // (rows, hq, 128) contiguous, input dtype
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;
@@ -150,12 +151,12 @@ struct alignas(16) BwdItem {
   int out_row0;  // row of the tile inside the owner's shard (== kv_row0 when not fused)
   int pad2;
 };
-// A query chunk that can see the key tile.  tile key j visible to chunk row i  iff  j <= i + diag.
+// A query chunk that can see the key tile.  tile key j visible to chunk row i  iff  i + lo <= j <= i + diag.
 struct alignas(16) BwdQSegment {
   int q_row0;  // first local row of the chunk
   int q_len;
   int diag;  // already relative to the key tile's first key
-  int pad;
+  int lo;    // sliding-window launches only (BwdParams::window != 0), relative like diag; otherwise ignored
 };
 
 struct BwdParams {
@@ -172,6 +173,7 @@ struct BwdParams {
   uint32_t ready_epoch;
   int n_items;
   int debug;  // bisecting aid: bit1 = no S^T look-ahead
+  int window;  // != 0: BwdQSegment::lo is meaningful (selects the kernel variant that masks the lower band edge)
   unsigned long long* trace;  // RFA_TRACE builds only
   PushParams push;
   SignalParams sig;

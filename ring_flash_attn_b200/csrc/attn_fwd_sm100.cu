@@ -97,9 +97,16 @@ __device__ __forceinline__ bool tile_needs_mask(const SegGeom& g, const WorkItem
   const bool diagonal = static_cast<long long>(jj) * kTile + (kTile - 1) > static_cast<long long>(first_row) + g.diag;
   return ragged || diagonal;
 }
+// Sliding window (kWindow kernels): key j of the segment is visible to chunk row i only if j >= i + lo.  The host
+// trims every segment per work item so that the loop still starts at key tile 0 (ops/attn_cuda.py); what remains
+// for the kernel is the slanted lower edge of the band.
+__device__ __forceinline__ bool tile_needs_lower_mask(int lo, const WorkItem& it, int t, int jj) {
+  const long long last_row = static_cast<long long>(it.q_off) + t * kTile + (kTile - 1);
+  return last_row + lo > static_cast<long long>(jj) * kTile;
+}
 
 // kPolyOf4: of every 4 element pairs, this many use the polynomial exp2 (0 = MUFU only)
-template <typename T, int kPolyOf4>
+template <typename T, int kPolyOf4, bool kWindow>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_ks,
@@ -355,6 +362,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool stamper = (threadIdx.x & 127) == 0;
       for (int si = 0; si < it.seg_count; ++si) {
         const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
+        int seg_lo = 0;
+        if constexpr (kWindow) seg_lo = p.seg_lo[it.seg_begin + si];
         for (int jj = 0; jj < g.n_tiles; ++jj, ++xi) {
           if (!tile_active(g, it, t, jj)) {
             turn_wait();
@@ -377,14 +386,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < 128; ++c) s[c] = __uint_as_float(sr[c]);
 
-          const bool masked = tile_needs_mask(g, it, t, jj);
+          bool masked = tile_needs_mask(g, it, t, jj);
+          if constexpr (kWindow) masked = masked || tile_needs_lower_mask(seg_lo, it, t, jj);
           if (masked) {
             long long lim_ll = static_cast<long long>(chunk_row) + g.diag;
             if (lim_ll > g.kv_len - 1) lim_ll = g.kv_len - 1;
             lim_ll -= static_cast<long long>(jj) * kTile;
             const int lim = lim_ll < -1 ? -1 : (lim_ll > 127 ? 127 : static_cast<int>(lim_ll));
+            if constexpr (kWindow) {
+              const long long lo_ll = static_cast<long long>(chunk_row) + seg_lo - static_cast<long long>(jj) * kTile;
+              const int lo_lim = lo_ll < 0 ? 0 : (lo_ll > 128 ? 128 : static_cast<int>(lo_ll));
 #pragma unroll
-            for (int c = 0; c < 128; ++c) s[c] = c <= lim ? s[c] : -CUDART_INF_F;
+              for (int c = 0; c < 128; ++c) s[c] = (c <= lim && c >= lo_lim) ? s[c] : -CUDART_INF_F;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 128; ++c) s[c] = c <= lim ? s[c] : -CUDART_INF_F;
+            }
           }
 
           float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
@@ -533,14 +550,17 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
     if (err == cudaSuccess) kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
   };
-  if (dtype == kDtypeBF16) {
-    if (poly == 0) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0>);
-    else if (poly == 1) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 1>);
-    else launch(fwd::attn_fwd_kernel<__nv_bfloat16, 2>);
+  if (p.seg_lo != nullptr) {  // sliding-window tables: the lower band edge is masked in-kernel
+    if (dtype == kDtypeBF16) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0, true>);
+    else launch(fwd::attn_fwd_kernel<__half, 0, true>);
+  } else if (dtype == kDtypeBF16) {
+    if (poly == 0) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0, false>);
+    else if (poly == 1) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 1, false>);
+    else launch(fwd::attn_fwd_kernel<__nv_bfloat16, 2, false>);
   } else {
-    if (poly == 0) launch(fwd::attn_fwd_kernel<__half, 0>);
-    else if (poly == 1) launch(fwd::attn_fwd_kernel<__half, 1>);
-    else launch(fwd::attn_fwd_kernel<__half, 2>);
+    if (poly == 0) launch(fwd::attn_fwd_kernel<__half, 0, false>);
+    else if (poly == 1) launch(fwd::attn_fwd_kernel<__half, 1, false>);
+    else launch(fwd::attn_fwd_kernel<__half, 2, false>);
   }
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();

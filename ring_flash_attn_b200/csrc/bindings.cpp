@@ -82,7 +82,7 @@ void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, co
 
 void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
                    const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
-                   const FusedCtx* fc) {
+                   const FusedCtx* fc, const at::Tensor* seg_lo = nullptr) {
   const c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(segs.scalar_type() == at::kInt && segs.is_cuda() && segs.is_contiguous() && segs.size(1) == 4);
@@ -93,6 +93,11 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   rfa::FwdParams p{};
   p.items = reinterpret_cast<const rfa::WorkItem*>(items.data_ptr());
   p.segs = reinterpret_cast<const rfa::KVSegment*>(segs.data_ptr());
+  if (seg_lo != nullptr) {
+    TORCH_CHECK(seg_lo->scalar_type() == at::kInt && seg_lo->is_cuda() && seg_lo->is_contiguous() &&
+                seg_lo->numel() == segs.size(0), "seg_lo must hold one int32 per segment");
+    p.seg_lo = seg_lo->data_ptr<int>();
+  }
   p.out = out.data_ptr();
   p.lse = lse.data_ptr<float>();
   p.lse_S = static_cast<int>(lse_S);
@@ -124,6 +129,13 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, con
   attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr);
 }
 
+// Sliding-window launch: seg_lo[i] is the lower band offset of segment i (see FwdParams::seg_lo).
+void attn_fwd_window(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+                     const at::Tensor& segs, const at::Tensor& seg_lo, at::Tensor& out, at::Tensor& lse, int64_t lse_S,
+                     double scale) {
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr, &seg_lo);
+}
+
 void attn_fwd_fused(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
                     const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
                     const FusedCtx& fc) {
@@ -140,7 +152,7 @@ void attn_bwd_delta(const at::Tensor& out, const at::Tensor& dout, at::Tensor& d
 void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
                    at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
                    const at::Tensor& delta, const c10::optional<at::Tensor>& dk, const c10::optional<at::Tensor>& dv,
-                   int64_t lse_S, double scale, const FusedCtx* fc) {
+                   int64_t lse_S, double scale, const FusedCtx* fc, bool window = false) {
   const c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(qsegs.scalar_type() == at::kInt && qsegs.is_cuda() && qsegs.is_contiguous() && qsegs.size(1) == 4);
@@ -167,6 +179,7 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
   TensorView dqv{dq_accum.data_ptr(), dq_accum.size(0), static_cast<int>(dq_accum.size(1)), dq_accum.stride(0),
                  dq_accum.stride(1)};
   p.n_items = static_cast<int>(items.size(0));
+  p.window = window ? 1 : 0;
   if (const char* e = std::getenv("RFA_B200_DEBUG")) p.debug = std::atoi(e);
   p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
   if (fc != nullptr) {
@@ -206,6 +219,13 @@ void attn_bwd(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, 
               at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
               const at::Tensor& delta, at::Tensor& dk, at::Tensor& dv, int64_t lse_S, double scale) {
   attn_bwd_impl(q, dout, k, v, dq_accum, items, qsegs, lse, delta, dk, dv, lse_S, scale, nullptr);
+}
+
+// Sliding-window launch: column 3 of qsegs carries the lower band offset (BwdQSegment::lo).
+void attn_bwd_window(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
+                     at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
+                     const at::Tensor& delta, at::Tensor& dk, at::Tensor& dv, int64_t lse_S, double scale) {
+  attn_bwd_impl(q, dout, k, v, dq_accum, items, qsegs, lse, delta, dk, dv, lse_S, scale, nullptr, true);
 }
 
 void attn_bwd_fused(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
@@ -313,6 +333,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("dkv_wait_epoch", &FusedCtx::dkv_wait_epoch);
   m.def("set_trace", &set_trace);
   m.def("attn_fwd", &attn_fwd);
+  m.def("attn_fwd_window", &attn_fwd_window);
+  m.def("attn_bwd_window", &attn_bwd_window);
   m.def("attn_fwd_fused", &attn_fwd_fused);
   m.def("attn_bwd_fused", &attn_bwd_fused);
   m.def("reduce_dkv", &reduce_dkv);

@@ -26,6 +26,22 @@ def _diag(d: Optional[int]) -> int:
     return DIAG_FULL if d is None else int(d)
 
 
+LO_NONE = -(1 << 29)  # "no lower bound" in the sliding-window tables
+
+
+def has_window(segs: Sequence[Segment]) -> bool:
+    return any(s.lo is not None for s in segs)
+
+
+def window_kernels_enabled() -> bool:
+    """Sliding-window plans run on the kernels only when asked for (``RFA_B200_WINDOW_KERNEL=1``): the kWindow
+    kernel variants were written after the last hardware session of round 1 and are validated in round 2;
+    until then windowed plans use the dense torch blocks (``parallel/engine.py``)."""
+    import os
+
+    return os.environ.get("RFA_B200_WINDOW_KERNEL", "0") == "1"
+
+
 # ----------------------------------------------------------------------------------------------
 # forward tables
 # ----------------------------------------------------------------------------------------------
@@ -57,6 +73,84 @@ def fwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int,
     items.sort(key=lambda t: -t[0])  # heaviest first
     covered = all((ci in by_chunk) or ch.rows == 0 for ci, ch in enumerate(plan.q_chunks))
     return [it for _, it in items], seg_rows, covered
+
+
+def fwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int]):
+    """Forward tables for sliding-window plans: (items, segments, seg_lo, all_rows_covered).
+
+    Key j of a segment is visible to chunk row i iff ``i + lo <= j <= i + diag``.  Every work item (256 query
+    rows starting at chunk row ``off``) gets its OWN copy of each segment, trimmed at the front to the first key
+    its first row can see (``off + lo``): the kernel's key loop then still starts at tile 0 and only has to mask
+    the slanted lower edge, for which ``seg_lo`` carries the re-based offset."""
+    by_chunk: Dict[int, List[Segment]] = {}
+    for s in segs:
+        by_chunk.setdefault(s.chunk, []).append(s)
+    items, seg_rows, seg_lo = [], [], []
+    covered = True
+    for ci, ch in enumerate(plan.q_chunks):
+        if ch.rows == 0:
+            continue
+        cs = by_chunk.get(ci)
+        if not cs:
+            covered = False
+            continue
+        for off in range(0, ch.rows, Q_ITEM_ROWS):
+            rows = min(Q_ITEM_ROWS, ch.rows - off)
+            begin = len(seg_rows)
+            work = 0
+            for s in cs:
+                j_min = 0 if s.lo is None else max(0, off + s.lo)
+                if j_min >= s.kv_len:
+                    continue  # even the first row's window starts behind the last key
+                if s.diag is not None and off + rows - 1 + s.diag < j_min:
+                    continue  # even the last row ends in front of the first key
+                d = DIAG_FULL if s.diag is None else s.diag - j_min
+                seg_rows.append([row_offset[s.src] + s.kv_row0 + j_min, s.kv_len - j_min, d, -1])
+                seg_lo.append(LO_NONE if s.lo is None else s.lo - j_min)
+                work += max(0, min(s.kv_len - j_min, off + rows + d))
+            if len(seg_rows) == begin:
+                covered = False  # nothing visible: out / lse of these rows keep their initial 0 / -inf
+                continue
+            items.append((work, [ch.row0 + off, rows, off, begin, len(seg_rows) - begin, 0, 0, 0]))
+    items.sort(key=lambda t: -t[0])
+    return [it for _, it in items], seg_rows, seg_lo, covered
+
+
+def bwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int]):
+    """Backward tables for sliding-window plans.  Same exclusive key tiles as :func:`bwd_tables_host`; a query
+    segment additionally carries ``lo`` (re-based to the tile's first key) and its length is cut behind the last
+    chunk row that can still see the tile's last key."""
+    by_src: Dict[int, List[Segment]] = {}
+    for s in segs:
+        by_src.setdefault(s.src, []).append(s)
+    items, qsegs = [], []
+    for src, ss in by_src.items():
+        cuts = sorted({s.kv_row0 for s in ss} | {s.kv_row0 + s.kv_len for s in ss})
+        for lo_cut, hi_cut in zip(cuts[:-1], cuts[1:]):
+            cover = [s for s in ss if s.kv_row0 <= lo_cut and s.kv_row0 + s.kv_len >= hi_cut]
+            for t0 in range(lo_cut, hi_cut, K_TILE_ROWS) if cover else ():
+                rows = min(K_TILE_ROWS, hi_cut - t0)
+                begin = len(qsegs)
+                work = 0
+                for s in cover:
+                    ch = plan.q_chunks[s.chunk]
+                    shift = t0 - s.kv_row0
+                    d = DIAG_FULL if s.diag is None else s.diag - shift
+                    q_len = ch.rows
+                    lo = LO_NONE
+                    if s.lo is not None:
+                        lo = s.lo - shift
+                        q_len = min(q_len, rows - lo)  # chunk row i sees tile key j iff i <= j - lo <= rows - 1 - lo
+                    first = max(0, -d)  # first chunk row that sees tile key 0
+                    if q_len <= 0 or first >= q_len:
+                        continue
+                    qsegs.append([ch.row0, q_len, d, lo])
+                    work += q_len - first
+                if len(qsegs) == begin:
+                    continue
+                items.append((work, [row_offset[src] + t0, rows, begin, len(qsegs) - begin, -1, 0, 0, 0]))
+    items.sort(key=lambda t: -t[0])
+    return [it for _, it in items], qsegs
 
 
 def bwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int],
@@ -193,8 +287,31 @@ def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None):
     return out, lse
 
 
+def _segments_forward_window(plan: CPPlan, segs: Sequence[Segment], q, k_src, v_src, scale):
+    C = cuda_ext.load()
+    src = segs[0].src
+    c = _cache(plan)
+    key = ("fwd_window", src, q.device.index)
+    if key not in c:
+        items, seg_rows, seg_lo, covered = fwd_tables_window_host(plan, segs, {src: 0})
+        c[key] = (_to_dev(items, 8, q.device), _to_dev(seg_rows if seg_rows else [[0, 0, 0, -1]], 4, q.device),
+                  torch.tensor(seg_lo if seg_lo else [LO_NONE], dtype=torch.int32).to(q.device), covered)
+    items, seg_t, lo_t, covered = c[key]
+    tq, hq, d = q.shape
+    out = (torch.empty if covered else torch.zeros)((tq, hq, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
+    if not covered:
+        lse.fill_(float("-inf"))
+    if items.shape[0]:
+        C.attn_fwd_window(_rows3(q), _rows3(k_src), _rows3(v_src), items, seg_t, lo_t, out, lse, tq, float(scale))
+        cuda_ext.note_launch()
+    return out, lse
+
+
 def segments_forward(plan: CPPlan, segs: Sequence[Segment], q, k_src, v_src, scale):
     """Partial attention of the local queries against ONE source shard (torch.distributed fallback path)."""
+    if has_window(segs):
+        return _segments_forward_window(plan, segs, q, k_src, v_src, scale)
     src = segs[0].src
     items, seg_t, covered = fwd_tables(plan, segs, {src: 0}, q.device, ("step", src))
     return forward_launch(q, k_src, v_src, items, seg_t, covered, scale)
@@ -221,5 +338,18 @@ def segments_backward(plan: CPPlan, segs: Sequence[Segment], dout, q, k_src, v_s
                       deterministic=False):
     """Gradient contribution of ONE source shard: dq (fp32) accumulates, dk/dv (fp32, zeroed) are filled."""
     src = segs[0].src
+    if has_window(segs):
+        C = cuda_ext.load()
+        c = _cache(plan)
+        key = ("bwd_window", src, q.device.index)
+        if key not in c:
+            items, qsegs = bwd_tables_window_host(plan, segs, {src: 0})
+            c[key] = (_to_dev(items, 8, q.device), _to_dev(qsegs if qsegs else [[0, 0, 0, 0]], 4, q.device))
+        items, qsegs = c[key]
+        if items.shape[0]:
+            C.attn_bwd_window(_rows3(q), _rows3(dout), _rows3(k_src), _rows3(v_src), dq, items, qsegs,
+                              lse.contiguous(), delta.contiguous(), dk, dv, q.shape[0], float(scale))
+            cuda_ext.note_launch()
+        return
     items, qsegs = bwd_tables(plan, segs, {src: 0}, q.device, ("step", src))
     backward_launch(q, dout, k_src, v_src, lse.contiguous(), delta.contiguous(), items, qsegs, scale, dq, dk, dv)

@@ -45,8 +45,7 @@ def _use_cuda_kernels(q: torch.Tensor, k: Optional[torch.Tensor] = None) -> bool
 
 
 def plan_has_window(plan: CPPlan) -> bool:
-    """Sliding-window plans carry a lower bound per segment; the sm_100a kernels do not implement it yet, so
-    such calls run the dense torch blocks (on whatever device the tensors live)."""
+    """Sliding-window plans carry a lower bound per segment."""
     cached = getattr(plan, "_has_window", None)
     if cached is None:
         cached = any(s.lo is not None for s in plan.segments)
@@ -54,11 +53,21 @@ def plan_has_window(plan: CPPlan) -> bool:
     return cached
 
 
+def _kernels_take(plan: CPPlan) -> bool:
+    """Windowed plans run on the kWindow kernel variants only with RFA_B200_WINDOW_KERNEL=1 (see
+    ``ops/attn_cuda.py:window_kernels_enabled``); otherwise on the dense torch blocks, on any device."""
+    if not plan_has_window(plan):
+        return True
+    from ..ops import attn_cuda
+
+    return attn_cuda.window_kernels_enabled()
+
+
 def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out, lse):
     """Fold the contribution of one source shard into the running (out, lse)."""
     if not segs:
         return out, lse
-    if _use_cuda_kernels(q, k_src) and not plan_has_window(plan):
+    if _use_cuda_kernels(q, k_src) and _kernels_take(plan):
         from ..ops import attn_cuda
 
         p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
@@ -82,7 +91,7 @@ def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse,
     dv = torch.zeros(v_src.shape, dtype=torch.float32, device=q.device)
     if not segs:
         return dk, dv
-    if _use_cuda_kernels(q, k_src) and not plan_has_window(plan):
+    if _use_cuda_kernels(q, k_src) and _kernels_take(plan):
         from ..ops import attn_cuda
 
         attn_cuda.segments_backward(plan, segs, dout, q, k_src, v_src, lse, delta, scale, dq, dk, dv,

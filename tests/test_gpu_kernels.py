@@ -200,3 +200,38 @@ def test_world1_small_head_dim_runs_on_kernels(d):
     assert out.shape == (1, 512, 4, d)
     torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
     assert (qkv.grad.float() - ref.grad).abs().max().item() < 5e-2 * ref.grad.abs().max().item() + 2e-2
+
+
+_EXPERIMENTAL = pytest.mark.skipif(
+    __import__("os").environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
+    reason="kernel variants written after the last hardware session; enable with RFA_B200_TEST_EXPERIMENTAL=1")
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("fn_name,causal,window", [
+    ("zigzag_ring_flash_attn_kvpacked_func", True, (100, 0)),
+    ("ring_flash_attn_kvpacked_func", True, (700, 0)),
+    ("stripe_flash_attn_kvpacked_func", True, (33, 0)),
+    ("ring_flash_attn_kvpacked_func", False, (150, 60)),
+    ("ring_flash_attn_kvpacked_func", False, (-1, 200)),
+])
+def test_sliding_window_kernels(monkeypatch, fn_name, causal, window):
+    """kWindow variants of both kernels (RFA_B200_WINDOW_KERNEL=1) against the windowed oracle."""
+    from ring_flash_attn_b200.ops import cuda_ext
+
+    monkeypatch.setenv("RFA_B200_WINDOW_KERNEL", "1")
+    torch.manual_seed(0)
+    q = torch.randn(2, 1000, 8, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    kv = torch.randn(2, 1000, 2, 2, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(2, 1000, 8, 128, device="cuda").to(torch.bfloat16)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    ref_out, ref_lse = attention_oracle(rq, rkv[:, :, 0], rkv[:, :, 1], causal, window_size=window)
+    ref_out.backward(dout.float())
+    before = cuda_ext.launch_counter().value
+    out, lse, _ = getattr(rfa, fn_name)(q, kv, causal=causal, window_size=window, return_attn_probs=True)
+    out.backward(dout)
+    assert cuda_ext.launch_counter().value >= before + 2, "windowed call did not reach the kernels"
+    torch.testing.assert_close(out.float(), ref_out, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
+    assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2

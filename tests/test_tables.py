@@ -113,3 +113,147 @@ def test_llama3_same_local_slice_different_global_layouts_do_not_share_caches():
     peers_a = api._llama3_peer_plan(pa[0]._rfa_llama3[0], True, 6, world, T)
     peers_b = api._llama3_peer_plan(pb[0]._rfa_llama3[0], True, 6, world, T)
     assert symm._ranges(peers_a, 0) and not symm._ranges(peers_b, 0)  # rank 6 needs rank 0's keys only in layout a
+
+
+# ----------------------------------------------------------------------------------------------
+# sliding window: replay the kernels' index arithmetic on the host tables and compare with the plan
+# ----------------------------------------------------------------------------------------------
+
+def _plan_visibility(plan, world):
+    """(q_rows, world * kv_rows) 0/1 matrix straight from the plan's segment semantics."""
+    vis = torch.zeros(plan.q_rows, world * plan.kv_rows, dtype=torch.int32)
+    for s in plan.segments:
+        ch = plan.q_chunks[s.chunk]
+        i = torch.arange(ch.rows).unsqueeze(1)
+        j = torch.arange(s.kv_len).unsqueeze(0)
+        m = torch.ones(ch.rows, s.kv_len, dtype=torch.bool)
+        if s.diag is not None:
+            m &= j <= i + s.diag
+        if s.lo is not None:
+            m &= j >= i + s.lo
+        c0 = s.src * plan.kv_rows + s.kv_row0
+        vis[ch.row0:ch.row0 + ch.rows, c0:c0 + s.kv_len] += m.int()
+    return vis
+
+
+def _replay_forward(items, segs, seg_lo, q_rows, kv_cols):
+    """attn_fwd_sm100.cu: seg_geom / tile_active / tile_needs_mask / tile_needs_lower_mask / the column limits."""
+    T = 128
+    vis = torch.zeros(q_rows, kv_cols, dtype=torch.int32)
+    for q_row0, n_rows, q_off, seg_begin, seg_count, *_ in items:
+        for si in range(seg_begin, seg_begin + seg_count):
+            kv_row0, kv_len, diag, _flag = segs[si]
+            lo = seg_lo[si]
+            last_row = q_off + n_rows - 1
+            reach = min(max(last_row + diag + 1, 0), kv_len)
+            n_tiles = (reach + T - 1) // T
+            for t in range(2):
+                n_t = min(n_rows, T) if t == 0 else n_rows - T
+                if n_t <= 0:
+                    continue
+                first_row = q_off + t * T
+                for jj in range(n_tiles):
+                    if not jj * T <= first_row + n_t - 1 + diag:  # tile_active
+                        continue
+                    masked = (jj + 1) * T > kv_len or jj * T + T - 1 > first_row + diag
+                    masked = masked or (first_row + T - 1 + lo > jj * T)
+                    for r in range(n_t):
+                        chunk_row = first_row + r
+                        c_lo, c_hi = 0, T - 1
+                        if masked:
+                            c_hi = max(-1, min(T - 1, min(chunk_row + diag, kv_len - 1) - jj * T))
+                            c_lo = max(0, min(T, chunk_row + lo - jj * T))
+                        if c_hi >= c_lo:
+                            a = kv_row0 + jj * T
+                            vis[q_row0 + t * T + r, a + c_lo:a + c_hi + 1] += 1
+    return vis
+
+
+def _replay_backward(items, qsegs, q_rows, kv_cols):
+    """attn_bwd_sm100.cu: q_geom, the lse=+inf rows behind q_len, q_lo / q_hi per key."""
+    TQ = 64
+    vis = torch.zeros(q_rows, kv_cols, dtype=torch.int32)
+    owner = torch.zeros(kv_cols, dtype=torch.int32)
+    for kv_row0, kv_rows, seg_begin, seg_count, *_ in items:
+        owner[kv_row0:kv_row0 + kv_rows] += 1
+        for q_row0, q_len, diag, lo in qsegs[seg_begin:seg_begin + seg_count]:
+            first = 0 if diag >= 0 else -diag
+            t_end = (q_len + TQ - 1) // TQ
+            t_begin = min(first // TQ, t_end)
+            for ti in range(t_begin, t_end):
+                for key in range(kv_rows):
+                    q_lo = max(0, min(TQ, key - diag - ti * TQ))
+                    last_q = key - lo - ti * TQ
+                    q_hi = 0 if last_q < 0 else (TQ if last_q >= TQ else last_q + 1)
+                    q_hi = min(q_hi, q_len - ti * TQ)  # rows behind q_len get lse = +inf from the stats warp
+                    if q_hi > q_lo:
+                        vis[q_row0 + ti * TQ + q_lo:q_row0 + ti * TQ + q_hi, kv_row0 + key] += 1
+    return vis, owner
+
+
+def _window_plans(scheme, world, window):
+    L = 600
+    if scheme == "ring":
+        return [P.plan_ring(r, world, 1, L, window[1] == 0, window) for r in range(world)]
+    if scheme == "zigzag":
+        return [P.plan_zigzag(r, world, 2, L, window) for r in range(world)]
+    if scheme == "stripe":
+        return [P.plan_stripe(r, world, 1, L, window) for r in range(world)]
+    cu = [0, 200, 520, 600]
+    if scheme == "ring_varlen":
+        return [P.plan_ring_varlen(r, world, cu, window[1] == 0, window) for r in range(world)]
+    return [P.plan_zigzag_varlen(r, world, cu, window) for r in range(world)]
+
+
+@pytest.mark.parametrize("scheme", ["ring", "zigzag", "stripe", "ring_varlen", "zigzag_varlen"])
+@pytest.mark.parametrize("world", [1, 4])
+@pytest.mark.parametrize("window", [(37, 0), (300, 0), (1000, 0)])
+def test_window_tables_replay_matches_plan(scheme, world, window):
+    for plan in _window_plans(scheme, world, window):
+        want = _plan_visibility(plan, world)
+        assert int(want.max()) <= 1
+        got_f = torch.zeros_like(want)
+        got_b = torch.zeros_like(want)
+        for src, segs in plan.by_src().items():
+            c0 = src * plan.kv_rows
+            if attn_cuda.has_window(segs):
+                items, seg_rows, seg_lo, covered = attn_cuda.fwd_tables_window_host(plan, segs, {src: 0})
+                b_items, b_qsegs = attn_cuda.bwd_tables_window_host(plan, segs, {src: 0})
+            else:
+                items, seg_rows, covered = attn_cuda.fwd_tables_host(plan, segs, {src: 0})
+                seg_lo = [attn_cuda.LO_NONE] * len(seg_rows)
+                b_items, b_qsegs = attn_cuda.bwd_tables_host(plan, segs, {src: 0})
+                b_qsegs = [[a, b, c, attn_cuda.LO_NONE] for a, b, c, _ in b_qsegs]
+            got_f[:, c0:c0 + plan.kv_rows] += _replay_forward(items, seg_rows, seg_lo, plan.q_rows, plan.kv_rows)
+            vb, owner = _replay_backward(b_items, b_qsegs, plan.q_rows, plan.kv_rows)
+            assert int(owner.max()) <= 1
+            got_b[:, c0:c0 + plan.kv_rows] += vb
+            # rows the forward items do not touch must be exactly the rows that see nothing from this source
+            touched = torch.zeros(plan.q_rows, dtype=torch.bool)
+            for q_row0, n_rows, *_ in items:
+                touched[q_row0:q_row0 + n_rows] = True
+            sees = want[:, c0:c0 + plan.kv_rows].sum(1) > 0
+            assert not bool((sees & ~touched).any())
+            assert covered == bool(touched.all())
+        assert torch.equal(got_f, want), "forward tables + kernel masks disagree with the plan"
+        assert torch.equal(got_b, want), "backward tables + kernel masks disagree with the plan"
+
+
+def test_window_two_sided_noncausal_replay():
+    for window in [(20, 9), (-1, 50), (130, -1)]:
+        for plan in [P.plan_ring(r, 4, 1, 300, False, window) for r in range(4)]:
+            want = _plan_visibility(plan, 4)
+            got_f, got_b = torch.zeros_like(want), torch.zeros_like(want)
+            for src, segs in plan.by_src().items():
+                c0 = src * plan.kv_rows
+                if attn_cuda.has_window(segs):
+                    items, seg_rows, seg_lo, _ = attn_cuda.fwd_tables_window_host(plan, segs, {src: 0})
+                    b_items, b_qsegs = attn_cuda.bwd_tables_window_host(plan, segs, {src: 0})
+                else:
+                    items, seg_rows, _ = attn_cuda.fwd_tables_host(plan, segs, {src: 0})
+                    seg_lo = [attn_cuda.LO_NONE] * len(seg_rows)
+                    b_items, b_qsegs = attn_cuda.bwd_tables_host(plan, segs, {src: 0})
+                    b_qsegs = [[a, b, c, attn_cuda.LO_NONE] for a, b, c, _ in b_qsegs]
+                got_f[:, c0:c0 + plan.kv_rows] += _replay_forward(items, seg_rows, seg_lo, plan.q_rows, plan.kv_rows)
+                got_b[:, c0:c0 + plan.kv_rows] += _replay_backward(b_items, b_qsegs, plan.q_rows, plan.kv_rows)[0]
+            assert torch.equal(got_f, want) and torch.equal(got_b, want)
