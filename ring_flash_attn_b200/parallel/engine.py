@@ -16,6 +16,7 @@ All tensors here are token-major: q ``(Tq,Hq,D)``, k/v ``(Tk,Hkv,D)``, lse ``(Hq
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -63,6 +64,27 @@ def _kernels_take(plan: CPPlan) -> bool:
     return attn_cuda.window_kernels_enabled()
 
 
+def _dense_tiles(row0: int, n_rows: int, s: Segment):
+    """Cut one (chunk x segment) block of the dense torch path into sub-blocks whose fp32 score matrix stays
+    small (``RFA_B200_DENSE_TILE`` query rows x 4x as many keys, default 1024 x 4096), so that the fallback for
+    shapes the kernels do not cover is slow but never allocates an S x S matrix.  Yields
+    (query rows, key rows, diag, lo) with the band offsets re-based to the sub-block; sub-blocks that lie
+    entirely outside the band are skipped."""
+    tq = max(1, int(os.environ.get("RFA_B200_DENSE_TILE", "1024")))
+    tk = 4 * tq
+    for oq in range(0, n_rows, tq):
+        nq = min(tq, n_rows - oq)
+        for ok in range(0, s.kv_len, tk):
+            nk = min(tk, s.kv_len - ok)
+            diag = None if s.diag is None else s.diag + oq - ok
+            lo = None if s.lo is None else s.lo + oq - ok
+            if diag is not None and diag + nq - 1 < 0:
+                continue  # even the last query row ends in front of this key block
+            if lo is not None and lo > nk - 1:
+                continue  # even the first query row starts behind it
+            yield (slice(row0 + oq, row0 + oq + nq), slice(s.kv_row0 + ok, s.kv_row0 + ok + nk), diag, lo)
+
+
 def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out, lse):
     """Fold the contribution of one source shard into the running (out, lse)."""
     if not segs:
@@ -77,10 +99,9 @@ def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out,
         lse = torch.full((q.shape[1], q.shape[0]), float("-inf"), dtype=torch.float32, device=q.device)
     for s in segs:
         ch = plan.q_chunks[s.chunk]
-        rows = slice(ch.row0, ch.row0 + ch.rows)
-        kv = slice(s.kv_row0, s.kv_row0 + s.kv_len)
-        b_out, b_lse = dense.block_fwd(q[rows], k_src[kv], v_src[kv], scale, s.diag, s.lo)
-        merge_partial(out, lse, b_out, b_lse, rows)
+        for rows, kv, diag, lo in _dense_tiles(ch.row0, ch.rows, s):
+            b_out, b_lse = dense.block_fwd(q[rows], k_src[kv], v_src[kv], scale, diag, lo)
+            merge_partial(out, lse, b_out, b_lse, rows)
     return out, lse
 
 
@@ -99,13 +120,12 @@ def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse,
         return dk, dv
     for s in segs:
         ch = plan.q_chunks[s.chunk]
-        rows = slice(ch.row0, ch.row0 + ch.rows)
-        kv = slice(s.kv_row0, s.kv_row0 + s.kv_len)
-        b_dq, b_dk, b_dv = dense.block_bwd(dout[rows], q[rows], k_src[kv], v_src[kv], lse[:, rows],
-                                           delta[:, rows], scale, s.diag, s.lo)
-        dq[rows] += b_dq
-        dk[kv] += b_dk
-        dv[kv] += b_dv
+        for rows, kv, diag, lo in _dense_tiles(ch.row0, ch.rows, s):
+            b_dq, b_dk, b_dv = dense.block_bwd(dout[rows], q[rows], k_src[kv], v_src[kv], lse[:, rows],
+                                               delta[:, rows], scale, diag, lo)
+            dq[rows] += b_dq
+            dk[kv] += b_dk
+            dv[kv] += b_dv
     return dk, dv
 
 

@@ -262,6 +262,19 @@ def _padded_head_dim_cases(rank, world):
     _llama3_case(rank, world, True, "none", 4, 2, 1)
 
 
+def _tiled_dense_cases(rank, world):
+    _batch_case(rank, world, "zigzag", True, "kv", 4, 2, torch.float32)
+    _batch_case(rank, world, "stripe", True, "qkv", 2, 2, torch.float32, (9, 0))
+    _varlen_case(rank, world, "ring", False, "none", 2, 1, (5, 3))
+    _llama3_case(rank, world, True, "qkv", 2, 2, 1)
+
+
+def test_dense_fallback_is_tiled(monkeypatch):
+    """RFA_B200_DENSE_TILE=3: every dense block is cut into 3 x 12 sub-blocks with re-based band offsets."""
+    monkeypatch.setenv("RFA_B200_DENSE_TILE", "3")
+    run_distributed(_tiled_dense_cases, 2)
+
+
 def test_head_dim_padding(monkeypatch):
     monkeypatch.setenv("RFA_B200_PAD_HEAD_DIM", "force")
     run_distributed(_padded_head_dim_cases, 2)
