@@ -1,6 +1,5 @@
 """Single-GPU kernel timings: sm_100a kernels vs flash_attn 2.8 (the kernel the reference calls)."""
 import json
-import math
 import os
 import sys
 

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import functools
 import os
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 

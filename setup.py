@@ -1,6 +1,6 @@
 """`python setup.py build_ext --inplace` (or `python -m ring_flash_attn_b200.build_ext`) builds the sm_100a
 extension next to the sources; `pip install -e .` installs the package in development mode."""
-from setuptools import Command, find_packages, setup
+from setuptools import find_packages, setup
 from setuptools.command.build_ext import build_ext as _build_ext
 
 

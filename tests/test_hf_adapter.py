@@ -2,7 +2,6 @@
 matches the same model run on the full sequence in one process (reference README.md:35-61 flow)."""
 import pytest
 import torch
-import torch.distributed as dist
 
 from dist_utils import run_distributed
 
