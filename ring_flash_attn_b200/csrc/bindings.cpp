@@ -142,6 +142,12 @@ void attn_fwd_fused(const at::Tensor& q, const at::Tensor& k, const at::Tensor& 
   attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, &fc);
 }
 
+void attn_fwd_fused_window(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+                           const at::Tensor& segs, const at::Tensor& seg_lo, at::Tensor& out, at::Tensor& lse,
+                           int64_t lse_S, double scale, const FusedCtx& fc) {
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, &fc, &seg_lo);
+}
+
 void attn_bwd_delta(const at::Tensor& out, const at::Tensor& dout, at::Tensor& delta, int64_t lse_S) {
   const c10::cuda::CUDAGuard guard(out.device());
   TORCH_CHECK(delta.is_contiguous() && delta.scalar_type() == at::kFloat);
@@ -232,6 +238,14 @@ void attn_bwd_fused(const at::Tensor& q, const at::Tensor& dout, const at::Tenso
                     at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs, const at::Tensor& lse,
                     const at::Tensor& delta, int64_t lse_S, double scale, const FusedCtx& fc) {
   attn_bwd_impl(q, dout, k, v, dq_accum, items, qsegs, lse, delta, c10::nullopt, c10::nullopt, lse_S, scale, &fc);
+}
+
+void attn_bwd_fused_window(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
+                           at::Tensor& dq_accum, const at::Tensor& items, const at::Tensor& qsegs,
+                           const at::Tensor& lse, const at::Tensor& delta, int64_t lse_S, double scale,
+                           const FusedCtx& fc) {
+  attn_bwd_impl(q, dout, k, v, dq_accum, items, qsegs, lse, delta, c10::nullopt, c10::nullopt, lse_S, scale, &fc,
+                true);
 }
 
 // Owner-side reduction of the dK/dV inbox (csrc/comm_sm100.cu).
@@ -336,6 +350,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_fwd_window", &attn_fwd_window);
   m.def("attn_bwd_window", &attn_bwd_window);
   m.def("attn_fwd_fused", &attn_fwd_fused);
+  m.def("attn_fwd_fused_window", &attn_fwd_fused_window);
+  m.def("attn_bwd_fused_window", &attn_bwd_fused_window);
   m.def("attn_bwd_fused", &attn_bwd_fused);
   m.def("reduce_dkv", &reduce_dkv);
   m.def("attn_bwd_delta", &attn_bwd_delta);

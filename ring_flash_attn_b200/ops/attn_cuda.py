@@ -75,7 +75,8 @@ def fwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int,
     return [it for _, it in items], seg_rows, covered
 
 
-def fwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int]):
+def fwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int],
+                           flag_of_src: Optional[Dict[int, int]] = None):
     """Forward tables for sliding-window plans: (items, segments, seg_lo, all_rows_covered).
 
     Key j of a segment is visible to chunk row i iff ``i + lo <= j <= i + diag``.  Every work item (256 query
@@ -105,7 +106,8 @@ def fwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Di
                 if s.diag is not None and off + rows - 1 + s.diag < j_min:
                     continue  # even the last row ends in front of the first key
                 d = DIAG_FULL if s.diag is None else s.diag - j_min
-                seg_rows.append([row_offset[s.src] + s.kv_row0 + j_min, s.kv_len - j_min, d, -1])
+                flag = -1 if flag_of_src is None else flag_of_src.get(s.src, -1)
+                seg_rows.append([row_offset[s.src] + s.kv_row0 + j_min, s.kv_len - j_min, d, flag])
                 seg_lo.append(LO_NONE if s.lo is None else s.lo - j_min)
                 work += max(0, min(s.kv_len - j_min, off + rows + d))
             if len(seg_rows) == begin:
@@ -116,14 +118,20 @@ def fwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Di
     return [it for _, it in items], seg_rows, seg_lo, covered
 
 
-def bwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int]):
+def bwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int, int],
+                           flag_of_src: Optional[Dict[int, int]] = None, fused: bool = False):
     """Backward tables for sliding-window plans.  Same exclusive key tiles as :func:`bwd_tables_host`; a query
     segment additionally carries ``lo`` (re-based to the tile's first key) and its length is cut behind the last
-    chunk row that can still see the tile's last key."""
+    chunk row that can still see the tile's last key.
+
+    ``fused=True`` follows :func:`bwd_tables_fused`: items carry owner / row-in-owner-shard, are emitted in ring
+    order, tiles without any query segment are kept (they store zeros into the owner's inbox), and the third
+    return value counts the tiles per owner."""
     by_src: Dict[int, List[Segment]] = {}
     for s in segs:
         by_src.setdefault(s.src, []).append(s)
     items, qsegs = [], []
+    per_owner = [0] * plan.world
     for src, ss in by_src.items():
         cuts = sorted({s.kv_row0 for s in ss} | {s.kv_row0 + s.kv_len for s in ss})
         for lo_cut, hi_cut in zip(cuts[:-1], cuts[1:]):
@@ -146,10 +154,16 @@ def bwd_tables_window_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Di
                         continue
                     qsegs.append([ch.row0, q_len, d, lo])
                     work += q_len - first
-                if len(qsegs) == begin:
-                    continue
-                items.append((work, [row_offset[src] + t0, rows, begin, len(qsegs) - begin, -1, 0, 0, 0]))
-    items.sort(key=lambda t: -t[0])
+                flag = -1 if flag_of_src is None else flag_of_src.get(src, -1)
+                if fused:
+                    step = (plan.rank - src) % plan.world
+                    items.append(((step, -work), [row_offset[src] + t0, rows, begin, len(qsegs) - begin, flag, src, t0, 0]))
+                    per_owner[src] += 1
+                elif len(qsegs) > begin:
+                    items.append(((0, -work), [row_offset[src] + t0, rows, begin, len(qsegs) - begin, flag, 0, 0, 0]))
+    items.sort(key=lambda t: t[0])
+    if fused:
+        return [it for _, it in items], qsegs, per_owner
     return [it for _, it in items], qsegs
 
 

@@ -279,7 +279,7 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
     if not _use_cuda_kernels(q, k):
         return False
-    if plan is not None and (not getattr(plan, "fused_ok", True) or plan_has_window(plan)):
+    if plan is not None and (not getattr(plan, "fused_ok", True) or not _kernels_take(plan)):
         return False
     from . import fused
 

@@ -260,14 +260,28 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
     ctx.ensure_stage(rows, k.shape[1], k.dtype)
     offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
     flags = {s: s for s in range(plan.world) if s != plan.rank}
-    items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, offsets, q.device, ("fused",), flags)
+    window = attn_cuda.has_window(plan.segments)
+    if window:
+        cache = attn_cuda._cache(plan)
+        key = ("fwd_fused_window", q.device.index)
+        if key not in cache:
+            it_h, seg_h, lo_h, cov = attn_cuda.fwd_tables_window_host(plan, plan.segments, offsets, flags)
+            cache[key] = (attn_cuda._to_dev(it_h, 8, q.device),
+                          attn_cuda._to_dev(seg_h if seg_h else [[0, 0, 0, -1]], 4, q.device),
+                          torch.tensor(lo_h if lo_h else [attn_cuda.LO_NONE], dtype=torch.int32).to(q.device), cov)
+        items, segs, seg_lo, covered = cache[key]
+    else:
+        items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, offsets, q.device, ("fused",), flags)
     fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hq)
     tq = q.shape[0]
     out = (torch.empty if covered else torch.zeros)((tq, hq, 128), dtype=q.dtype, device=q.device)
     lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
     if not covered:
         lse.fill_(float("-inf"))
-    C.attn_fwd_fused(attn_cuda._rows3(q), k, v, items, segs, out, lse, tq, float(scale), fc)
+    if window:
+        C.attn_fwd_fused_window(attn_cuda._rows3(q), k, v, items, segs, seg_lo, out, lse, tq, float(scale), fc)
+    else:
+        C.attn_fwd_fused(attn_cuda._rows3(q), k, v, items, segs, out, lse, tq, float(scale), fc)
     cuda_ext.note_launch()
     return out, lse
 
@@ -305,7 +319,17 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     ctx.ensure_inbox(rows, hkv)
     offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
     flags = {s: s for s in range(plan.world) if s != plan.rank}
-    items, qsegs, per_owner = attn_cuda.bwd_tables_fused(plan, offsets, q.device, flags)
+    window = attn_cuda.has_window(plan.segments)
+    if window:
+        cache = attn_cuda._cache(plan)
+        key = ("bwd_fused_window", q.device.index)
+        if key not in cache:
+            it_h, qs_h, per = attn_cuda.bwd_tables_window_host(plan, plan.segments, offsets, flags, fused=True)
+            cache[key] = (attn_cuda._to_dev(it_h, 8, q.device),
+                          attn_cuda._to_dev(qs_h if qs_h else [[0, 0, 0, 0]], 4, q.device), per)
+        items, qsegs, per_owner = cache[key]
+    else:
+        items, qsegs, per_owner = attn_cuda.bwd_tables_fused(plan, offsets, q.device, flags)
     delta = attn_cuda.compute_delta(out, dout)
     dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
     fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hkv)
@@ -316,8 +340,9 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
         ctx.dkv_cum[o] = (ctx.dkv_cum[o] + per_owner[o] * hkv) & MASK32
     fc.dkv_targets = list(ctx.dkv_cum)
     fc.dkv_wait_epoch = ctx.last_bwd_epoch
-    C.attn_bwd_fused(attn_cuda._rows3(q), attn_cuda._rows3(dout), k, v, dq, items, qsegs, lse.contiguous(), delta,
-                     q.shape[0], float(scale), fc)
+    launch = C.attn_bwd_fused_window if window else C.attn_bwd_fused
+    launch(attn_cuda._rows3(q), attn_cuda._rows3(dout), k, v, dq, items, qsegs, lse.contiguous(), delta,
+           q.shape[0], float(scale), fc)
     cuda_ext.note_launch()
     # owner-side reduction of the inbox (waits for the peers' "gradients landed" epochs on the device)
     tasks = reduce_tasks(plan, ctx, q.device)

@@ -18,3 +18,5 @@ for impl in ours reference; do
   timeout 900 $TR --master-port 29543 benchmark/bench_configs.py --impl $impl > gpurun_out/bench_configs_${impl}_$N.jsonl 2> gpurun_out/bench_configs_${impl}_$N.err
   grep '^{' gpurun_out/bench_configs_${impl}_$N.jsonl | cut -c1-260
 done
+echo "== experimental kernel variants written after the last round-1 hardware session (sliding window)"
+RFA_B200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_multi.py -m gpu -q --timeout 600 -k "sliding_window_kernels" > gpurun_out/pytest_window.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_window.log

@@ -153,3 +153,41 @@ def test_varlen_schemes_2gpu(p2p):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     run_distributed(_all_varlen_cases, 2, p2p, backend="nccl")
+
+
+def _window_fused_case(rank, world, p2p):
+    os.environ["RFA_B200_WINDOW_KERNEL"] = "1"
+    os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    S, H, HK, d = 1024 * world, 8, 2, 128
+    for scheme, window in (("zigzag", (300, 0)), ("ring", (1500, 0)), ("stripe", (77, 0))):
+        q = torch.randn(1, S, H, d, device=dev).to(torch.bfloat16)
+        kv = torch.randn(1, S, 2, HK, d, device=dev).to(torch.bfloat16)
+        dout = torch.randn(1, S, H, d, device=dev).to(torch.bfloat16)
+        for t in (q, kv, dout):
+            dist.broadcast(t, src=0)
+        rq, rkv = q.float().requires_grad_(True), kv.float().requires_grad_(True)
+        ref, _ = attention_oracle(rq, rkv[:, :, 0], rkv[:, :, 1], True, window_size=window)
+        ref.backward(dout.float())
+        shard = getattr(layouts, f"shard_{scheme}")
+        lq = shard(q, rank, world).detach().requires_grad_(True)
+        lkv = shard(kv, rank, world).detach().requires_grad_(True)
+        fn = getattr(rfa, {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}[scheme] + "_flash_attn_kvpacked_func")
+        for _ in range(2):  # second call exercises buffer reuse / epochs
+            lq.grad = lkv.grad = None
+            out = fn(lq, lkv, causal=True, window_size=window)
+            out.backward(shard(dout, rank, world))
+        torch.testing.assert_close(out.float(), shard(ref, rank, world), atol=2e-2, rtol=2e-2)
+        gq, gkv = shard(rq.grad, rank, world), shard(rkv.grad, rank, world)
+        assert (lq.grad.float() - gq).abs().max().item() < 5e-2 * gq.abs().max().item() + 2e-2
+        assert (lkv.grad.float() - gkv).abs().max().item() < 5e-2 * gkv.abs().max().item() + 2e-2
+
+
+@pytest.mark.skipif(__import__("os").environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="kWindow kernel variants are validated in round 2 (RFA_B200_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("p2p", [True, False])
+def test_sliding_window_kernels_2gpu(p2p):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_window_fused_case, 2, p2p, backend="nccl")

@@ -257,3 +257,39 @@ def test_window_two_sided_noncausal_replay():
                 got_f[:, c0:c0 + plan.kv_rows] += _replay_forward(items, seg_rows, seg_lo, plan.q_rows, plan.kv_rows)
                 got_b[:, c0:c0 + plan.kv_rows] += _replay_backward(b_items, b_qsegs, plan.q_rows, plan.kv_rows)[0]
             assert torch.equal(got_f, want) and torch.equal(got_b, want)
+
+
+@pytest.mark.parametrize("scheme", ["zigzag", "ring", "stripe", "zigzag_varlen"])
+@pytest.mark.parametrize("window", [(90, 0), (700, 0)])
+def test_window_fused_tables(scheme, window):
+    """Fused multi-GPU layout of the windowed tables: one launch over all sources (local tensor for flag -1,
+    staging slot of the source otherwise), backward tiles for every key row a peer will reduce, per-owner counts."""
+    world = 4
+    plans = _window_plans(scheme, world, window)
+    for p in plans:
+        rows = p.kv_rows
+        offsets = {s: (0 if s == p.rank else s * rows) for s in range(world)}
+        flags = {s: s for s in range(world) if s != p.rank}
+        want = _plan_visibility(p, world)
+        items, seg_rows, seg_lo, _cov = attn_cuda.fwd_tables_window_host(p, p.segments, offsets, flags)
+        glob = []
+        for kv_row0, kv_len, d, flag in seg_rows:
+            src = p.rank if flag < 0 else flag
+            assert offsets[src] <= kv_row0 and kv_row0 + kv_len <= offsets[src] + rows
+            glob.append([src * rows + kv_row0 - offsets[src], kv_len, d, flag])
+        assert torch.equal(_replay_forward(items, glob, seg_lo, p.q_rows, world * rows), want)
+
+        b_items, b_qsegs, per_owner = attn_cuda.bwd_tables_window_host(p, p.segments, offsets, flags, fused=True)
+        assert sum(per_owner) == len(b_items)
+        g_items = []
+        for kv_row0, kv_rows, b, c, flag, owner, out_row0, z in b_items:
+            assert (flag < 0) == (owner == p.rank) and kv_row0 - offsets[owner] == out_row0
+            g_items.append([owner * rows + out_row0, kv_rows, b, c, flag, owner, out_row0, z])
+        vb, owner_rows = _replay_backward(g_items, b_qsegs, p.q_rows, world * rows)
+        assert torch.equal(vb, want) and int(owner_rows.max()) <= 1
+        # every key row that an owner's reduction will read from this rank's slot is written by exactly one tile
+        expect = torch.zeros(world * rows, dtype=torch.int32)
+        for s in range(world):
+            for lo, hi in symm._ranges(p, s):
+                expect[s * rows + lo:s * rows + hi] = 1
+        assert torch.equal(owner_rows, expect)
