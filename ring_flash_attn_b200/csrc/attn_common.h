@@ -207,6 +207,8 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
                             const TensorView& dq_accum, const BwdParams& p, cudaStream_t stream);
 const char* probe_launch(const TensorView& a, const TensorView& b, const void* a_raw, const void* b_raw, float* out,
                          const ProbeConfig& c, cudaStream_t stream);
+const char* probe_fp8_launch(const TensorView& a, const TensorView& b, float* out, const ProbeConfig& c,
+                             cudaStream_t stream);
 const char* lse_flatten_launch(const float* in, float* out, const int* cu, int batch, int heads, int max_seqlen,
                                int total, cudaStream_t stream);
 const char* lse_unflatten_launch(const float* in, float* out, const int* cu, int batch, int heads, int max_seqlen,

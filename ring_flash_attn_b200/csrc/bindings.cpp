@@ -273,6 +273,31 @@ void reduce_dkv(const at::Tensor& inbox, int64_t slot_stride, int64_t kv_stride,
   check(rfa::reduce_dkv_launch(dtype_code(dk), p, at::cuda::getCurrentCUDAStream()));
 }
 
+// kind::f8f6f4 descriptor probe (csrc/probe_fp8_sm100.cu): a, b are (128, 128) float8_e4m3fn tensors;
+// cfg = {a_kind (0 smem K-major, 1 TMEM), b_kind (0 K-major, 1 MN-major), tmem byte order, lbo_b, sbo_b, kstep_b}
+at::Tensor probe_fp8(const at::Tensor& a, const at::Tensor& b, std::vector<int64_t> cfg) {
+  const c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(cfg.size() == 6);
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && a.element_size() == 1 && b.element_size() == 1 &&
+              a.numel() == 128 * 128 && b.numel() == 128 * 128);
+  rfa::ProbeConfig c{};
+  c.a_kind = static_cast<int>(cfg[0]);
+  c.b_kind = static_cast<int>(cfg[1]);
+  c.n = 128;
+  c.kdim = 128;
+  c.lbo_a = static_cast<int>(cfg[2]);
+  c.sbo_a = c.kstep_a = -1;
+  c.lbo_b = static_cast<int>(cfg[3]);
+  c.sbo_b = static_cast<int>(cfg[4]);
+  c.kstep_b = static_cast<int>(cfg[5]);
+  c.reps = 1;
+  c.cycles = nullptr;
+  TensorView va{a.data_ptr(), 128, 1, 128, 128}, vb{b.data_ptr(), 128, 1, 128, 128};
+  at::Tensor out = at::zeros({128, 128}, a.options().dtype(at::kFloat));
+  check(rfa::probe_fp8_launch(va, vb, out.data_ptr<float>(), c, at::cuda::getCurrentCUDAStream()));
+  return out;
+}
+
 at::Tensor probe(const at::Tensor& a, const at::Tensor& b, std::vector<int64_t> cfg) {
   // a: (rows, 128) or (128, kdim) bf16 ; b likewise; cfg = {a_kind, b_kind, n, kdim, lbo_a, sbo_a, kstep_a, lbo_b, sbo_b, kstep_b}
   const c10::cuda::CUDAGuard guard(a.device());
@@ -357,6 +382,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_bwd_delta", &attn_bwd_delta);
   m.def("attn_bwd", &attn_bwd);
   m.def("probe", &probe);
+  m.def("probe_fp8", &probe_fp8);
   m.def("lse_flatten", &lse_flatten);
   m.def("lse_unflatten", &lse_unflatten);
   rfa::bind_peer_mem(m);

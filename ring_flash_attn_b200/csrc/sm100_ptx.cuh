@@ -209,6 +209,47 @@ __device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint3
       "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- kind::f8f6f4 (e4m3 / e5m2 operands, fp32 accumulate, K = 32 per instruction) ----------------------
+// Same instruction-descriptor layout as kind::f16; the format fields select the 8-bit type
+// (0 = e4m3, 1 = e5m2).  MN-major operands are legal for the 8-bit float types.
+__host__ __device__ constexpr uint32_t umma_idesc_f8(uint32_t a_fmt, uint32_t b_fmt, uint32_t m, uint32_t n,
+                                                     uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss2_f8(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts2_f8(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// four fp32 -> four e4m3 in one 32-bit word, element 0 in the least significant byte (saturating)
+__device__ __forceinline__ uint32_t pack4_e4m3(float f0, float f1, float f2, float f3) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}\n"
+      : "=r"(r)
+      : "f"(f0), "f"(f1), "f"(f2), "f"(f3));
+  return r;
+}
+
 // All MMAs issued so far by this thread arrive on `bar` when they complete.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -242,6 +283,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};" ::RFA_W8(r, 0),
       RFA_W8(r, 8), RFA_W8(r, 16), RFA_W8(r, 24), "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::RFA_W8(r, 0),
+               "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(

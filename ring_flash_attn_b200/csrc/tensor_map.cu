@@ -34,7 +34,9 @@ const char* make_tensor_map(CUtensorMap* out, const TensorView& t, int elem_byte
                            static_cast<cuuint64_t>(t.row_stride) * elem_bytes};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(box_inner), 1u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMapDataType dt = elem_bytes == 4   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8  // fp8: 128 one-byte elements per span
+                                             : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = encode(out, dt, 3, t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
