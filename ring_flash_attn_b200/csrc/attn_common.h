@@ -126,6 +126,8 @@ struct FwdParams {
   const WorkItem* items;
   const KVSegment* segs;
   const int* seg_lo;  // sliding window only (else nullptr): per segment, key j visible to chunk row i iff j >= i + lo
+  const float* head_scale_qk;  // fp8 only: q_descale * k_descale per QUERY head (multiplies the softmax scale)
+  const float* head_scale_v;   // fp8 only: v_descale per KV head (multiplies the output)
   void* out;  // (rows, hq, 128) contiguous, input dtype
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;
@@ -192,7 +194,7 @@ struct ProbeConfig {
 };
 
 // dtype codes shared with the Python side
-enum : int { kDtypeBF16 = 0, kDtypeFP16 = 1 };
+enum : int { kDtypeBF16 = 0, kDtypeFP16 = 1, kDtypeE4M3 = 2 };
 
 // ---- launchers (implemented in the .cu files; plain C++ so bindings.cpp needs no CUDA headers beyond runtime)
 // k_stage / v_stage: the peer-filled staging tensors read by segments with flag >= 0 (pass k / v when unused).

@@ -67,6 +67,27 @@ struct Barriers {
 
 constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
 
+// Element traits.  Fp8E4M3 is the tag of the experimental fp8 forward (RFA_B200_FP8_KERNEL=1): q / k / v are e4m3
+// bytes, a tile is ONE 128-byte swizzle span per row (16 KB, loaded into the same 32 KB slots), both GEMMs are
+// kind::f8f6f4 with K = 32 per instruction, P is written back to tensor memory as e4m3 (four per column) and the
+// output is bf16.  Per-head descales (q*k folded into the softmax scale, v applied in the epilogue) come in
+// through FwdParams::head_scale_qk / head_scale_v.
+struct Fp8E4M3 {};
+template <typename T>
+struct Elem {
+  static constexpr bool kFp8 = false;
+  static constexpr uint32_t kTxBytes = kTileBytes;
+  static constexpr uint32_t kFmt = Pack2<T>::kFmt;
+  using Out = T;
+};
+template <>
+struct Elem<Fp8E4M3> {
+  static constexpr bool kFp8 = true;
+  static constexpr uint32_t kTxBytes = kTile * kD;
+  static constexpr uint32_t kFmt = 0;  // e4m3
+  using Out = __nv_bfloat16;
+};
+
 // Per-(item, segment) geometry shared by all roles so that they agree on the iteration space.
 struct SegGeom {
   int kv_row0, kv_len, diag;
@@ -122,6 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     return;
   }
+  using E = Elem<T>;
   const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -168,13 +190,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
    if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->q_full[0], kTileBytes);
+      mbar_arrive_expect_tx(&bars->q_full[0], E::kTxBytes);
       tma_load_3d(smem_q, &tm_q, &bars->q_full[0], 0, head, it.q_row0);
-      tma_load_3d(smem_q + kHalfBytes, &tm_q, &bars->q_full[0], 64, head, it.q_row0);
+      if constexpr (!E::kFp8) tma_load_3d(smem_q + kHalfBytes, &tm_q, &bars->q_full[0], 64, head, it.q_row0);
       if (has_t1) {
-        mbar_arrive_expect_tx(&bars->q_full[1], kTileBytes);
+        mbar_arrive_expect_tx(&bars->q_full[1], E::kTxBytes);
         tma_load_3d(smem_q + kTileBytes, &tm_q, &bars->q_full[1], 0, head, it.q_row0 + kTile);
-        tma_load_3d(smem_q + kTileBytes + kHalfBytes, &tm_q, &bars->q_full[1], 64, head, it.q_row0 + kTile);
+        if constexpr (!E::kFp8)
+          tma_load_3d(smem_q + kTileBytes + kHalfBytes, &tm_q, &bars->q_full[1], 64, head, it.q_row0 + kTile);
       }
       uint32_t slot = 0, phase = 0;
       for (int si = 0; si < it.seg_count; ++si) {
@@ -191,9 +214,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(&bars->kv_empty[slot], phase ^ 1);
             uint8_t* dst = smem_kv + slot * kTileBytes;
             const CUtensorMap* tm = staged ? (kv == 0 ? &tm_ks : &tm_vs) : (kv == 0 ? &tm_k : &tm_v);
-            mbar_arrive_expect_tx(&bars->kv_full[slot], kTileBytes);
+            mbar_arrive_expect_tx(&bars->kv_full[slot], E::kTxBytes);
             tma_load_3d(dst, tm, &bars->kv_full[slot], 0, kv_head, row);
-            tma_load_3d(dst + kHalfBytes, tm, &bars->kv_full[slot], 64, kv_head, row);
+            if constexpr (!E::kFp8) tma_load_3d(dst + kHalfBytes, tm, &bars->kv_full[slot], 64, kv_head, row);
             if (++slot == kStages) {
               slot = 0;
               phase ^= 1;
@@ -208,8 +231,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // issues the tcgen05 instructions and commits.
     {
       const bool leader = elect_one();
-      constexpr uint32_t idesc_qk = umma_idesc_f16(Pack2<T>::kFmt, kTile, kTile, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(Pack2<T>::kFmt, kTile, kD, 0, 1);
+      constexpr uint32_t idesc_qk = E::kFp8 ? umma_idesc_f8(E::kFmt, E::kFmt, kTile, kTile, 0, 0)
+                                            : umma_idesc_f16(E::kFmt, kTile, kTile, 0, 0);
+      constexpr uint32_t idesc_pv = E::kFp8 ? umma_idesc_f8(E::kFmt, E::kFmt, kTile, kD, 0, 1)
+                                            : umma_idesc_f16(E::kFmt, kTile, kD, 0, 1);
       const uint32_t q_base = smem_u32(smem_q);
       const uint32_t kv_base = smem_u32(smem_kv);
       const uint32_t col_s[2] = {tmem + kColS0, tmem + kColS1};
@@ -224,10 +249,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
       auto issue_qk = [&](int t, uint32_t k_slot) {
         const uint32_t a0 = q_lo[t], b0 = k_lo0 + k_slot * slot_step;
+        if constexpr (E::kFp8) {
+          // one 128-byte span per row holds all 128 head dims: 4 instructions of K = 32 bytes
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
-          umma_ss2(col_s[t], a0 + off, hi, b0 + off, hi, idesc_qk, k > 0);
+          for (int k = 0; k < kD / 32; ++k)
+            umma_ss2_f8(col_s[t], a0 + ((k * 32) >> 4), hi, b0 + ((k * 32) >> 4), hi, idesc_qk, k > 0);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) {
+            const uint32_t off = ((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4;
+            umma_ss2(col_s[t], a0 + off, hi, b0 + off, hi, idesc_qk, k > 0);
+          }
         }
         umma_commit(&bars->s_full[t]);
       };
@@ -235,9 +267,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // V tile is [128 keys][2 x 64 dims] -> MN-major B: LBO = stride between the two 64-wide halves,
         // SBO = stride between 8-key groups; one MMA consumes 16 keys = 2048 bytes.
         const uint32_t b0 = v_lo0 + v_slot * slot_step;
+        if constexpr (E::kFp8) {
+          // e4m3: the 128 dims of a key are one span (no second half, LBO unused); one instruction consumes 32
+          // keys = 4096 bytes of V and 32 packed P values = 8 TMEM columns
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)
-          umma_ts2(col_o[t], col_s[t] + k * 8, b0 + k * (2048 >> 4), hi, idesc_pv, (accumulate || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kTile / 32; ++k)
+            umma_ts2_f8(col_o[t], col_s[t] + k * 8, b0 + k * (4096 >> 4), hi, idesc_pv,
+                        (accumulate || k > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k)
+            umma_ts2(col_o[t], col_s[t] + k * 8, b0 + k * (2048 >> 4), hi, idesc_pv,
+                     (accumulate || k > 0) ? 1u : 0u);
+        }
       };
 
       mbar_wait(&bars->q_full[0], 0);
@@ -333,6 +375,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t t_o = tmem + (t == 0 ? kColO0 : kColO1) + lane_addr;
     const int chunk_row = it.q_off + t * kTile + row_in_tile;  // row index inside the chunk (diagonal space)
 
+    // fp8: the per-head q*k descale rides on the softmax scale
+    float scale = p.scale, scale_log2 = p.scale_log2;
+    if constexpr (E::kFp8) {
+      const float hs = p.head_scale_qk[head];
+      scale *= hs;
+      scale_log2 *= hs;
+    }
     float m_ref = -CUDART_INF_F;  // reference max (raw score units)
     float l = 0.f;
     bool first = true;
@@ -414,9 +463,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
           // lazy rescale: only move the reference max when it grew by more than the threshold
-          const bool need = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
+          const bool need = (m_new - m_ref) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            const float f = need ? fast_exp2((m_ref - m_new) * p.scale_log2) : 1.0f;
+            const float f = need ? fast_exp2((m_ref - m_new) * scale_log2) : 1.0f;
             if (need) {
               l *= f;
               m_ref = m_new;
@@ -435,18 +484,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
           first = false;
-          const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * p.scale_log2;
+          const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * scale_log2;
           turn_wait();
           RFA_STAMP(stamper, xi, 8 + 5 * t);
           // exp2(s * c - m * c) on packed pairs.  MUFU.EX2 alone (16 lanes per SM) would cost 1024 cycles per
           // 128x128 tile per warp and bound the whole kernel, so kPolyOf4 of every 4 pairs are evaluated with
           // a polynomial on the FMA pipes instead (masked tiles keep exact zeros by staying on the MUFU path).
-          const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nmc2 = pack2(-mc, -mc);
+          const uint64_t sc2 = pack2(scale_log2, scale_log2), nmc2 = pack2(-mc, -mc);
           uint64_t lsum = pack2(0.f, 0.f);
           auto exp_chunks = [&](auto use_poly) {
 #pragma unroll
             for (int c = 0; c < 128; c += 32) {
               uint32_t pk[16];
+              [[maybe_unused]] float pe0 = 0.f, pe1 = 0.f;  // fp8 only: the even pair waiting for its odd partner
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const uint64_t x = ffma2(pack2(s[c + 2 * i], s[c + 2 * i + 1]), sc2, nmc2);
@@ -460,9 +510,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                   e1 = fast_exp2(x1);
                 }
                 lsum = fadd2(lsum, pack2(e0, e1));
-                pk[i] = Pack2<T>::pack(e0, e1);
+                if constexpr (E::kFp8) {
+                  if (i & 1) {
+                    pk[i >> 1] = pack4_e4m3(pe0, pe1, e0, e1);
+                  } else {
+                    pe0 = e0;
+                    pe1 = e1;
+                  }
+                } else {
+                  pk[i] = Pack2<T>::pack(e0, e1);
+                }
               }
-              tmem_st16(t_s + (c >> 1), pk);
+              if constexpr (E::kFp8) {
+                tmem_st8(t_s + (c >> 2), pk);  // 32 e4m3 = 8 columns per 32 scores
+              } else {
+                tmem_st16(t_s + (c >> 1), pk);
+              }
             }
           };
           if (masked) {
@@ -485,11 +548,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---------------------------------------------------------------- epilogue: O / l -> out, lse
       const int row = it.q_row0 + t * kTile + row_in_tile;
       const bool row_ok = row_in_tile < n_rows;
-      T* out_row = reinterpret_cast<T*>(p.out) + (static_cast<size_t>(row) * p.hq + head) * kD;
+      using OutT = typename E::Out;
+      OutT* out_row = reinterpret_cast<OutT*>(p.out) + (static_cast<size_t>(row) * p.hq + head) * kD;
       if (!first) {
         mbar_wait(&bars->o_done[t], 0);
         tc_fence_after();
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        float inv = l > 0.f ? 1.0f / l : 0.f;
+        if constexpr (E::kFp8) inv *= p.head_scale_v[kv_head];
 #pragma unroll
         for (int c = 0; c < 128; c += 32) {
           uint32_t orr[32];
@@ -499,10 +564,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               uint4 v;
-              v.x = Pack2<T>::pack(__uint_as_float(orr[i + 0]) * inv, __uint_as_float(orr[i + 1]) * inv);
-              v.y = Pack2<T>::pack(__uint_as_float(orr[i + 2]) * inv, __uint_as_float(orr[i + 3]) * inv);
-              v.z = Pack2<T>::pack(__uint_as_float(orr[i + 4]) * inv, __uint_as_float(orr[i + 5]) * inv);
-              v.w = Pack2<T>::pack(__uint_as_float(orr[i + 6]) * inv, __uint_as_float(orr[i + 7]) * inv);
+              v.x = Pack2<OutT>::pack(__uint_as_float(orr[i + 0]) * inv, __uint_as_float(orr[i + 1]) * inv);
+              v.y = Pack2<OutT>::pack(__uint_as_float(orr[i + 2]) * inv, __uint_as_float(orr[i + 3]) * inv);
+              v.z = Pack2<OutT>::pack(__uint_as_float(orr[i + 4]) * inv, __uint_as_float(orr[i + 5]) * inv);
+              v.w = Pack2<OutT>::pack(__uint_as_float(orr[i + 6]) * inv, __uint_as_float(orr[i + 7]) * inv);
               *reinterpret_cast<uint4*>(out_row + c + i) = v;
             }
           }
@@ -513,7 +578,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(out_row + c) = z;
       }
       if (row_ok) {
-        const float lse = l > 0.f ? m_ref * p.scale + __logf(l) : -CUDART_INF_F;
+        const float lse = l > 0.f ? m_ref * scale + __logf(l) : -CUDART_INF_F;
         const size_t b = row / p.lse_S, sidx = row % p.lse_S;
         p.lse[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx] = lse;
       }
@@ -534,11 +599,14 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
   const int n_blocks = p.push.n_ctas + p.n_items * p.hq;
   if (n_blocks <= 0) return nullptr;
   CUtensorMap tq, tk, tv, tks, tvs;
-  if (const char* e = make_tensor_map(&tq, q, 2, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tk, k, 2, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tv, v, 2, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tks, k_stage, 2, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tvs, v_stage, 2, fwd::kTile, fwd::kD)) return e;
+  const int eb = dtype == kDtypeE4M3 ? 1 : 2;
+  if (dtype == kDtypeE4M3 && (p.head_scale_qk == nullptr || p.head_scale_v == nullptr || p.seg_lo != nullptr))
+    return "fp8 forward needs per-head descales and does not support sliding windows yet";
+  if (const char* e = make_tensor_map(&tq, q, eb, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tk, k, eb, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tv, v, eb, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tks, k_stage, eb, fwd::kTile, fwd::kD)) return e;
+  if (const char* e = make_tensor_map(&tvs, v_stage, eb, fwd::kTile, fwd::kD)) return e;
   dim3 grid(n_blocks, 1, 1), block(fwd::kThreads, 1, 1);
   cudaError_t err = cudaSuccess;
   static const int poly = [] {
@@ -550,7 +618,9 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
     if (err == cudaSuccess) kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
   };
-  if (p.seg_lo != nullptr) {  // sliding-window tables: the lower band edge is masked in-kernel
+  if (dtype == kDtypeE4M3) {  // experimental fp8 forward (e4m3 in, bf16 out)
+    launch(fwd::attn_fwd_kernel<fwd::Fp8E4M3, 0, false>);
+  } else if (p.seg_lo != nullptr) {  // sliding-window tables: the lower band edge is masked in-kernel
     if (dtype == kDtypeBF16) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0, true>);
     else launch(fwd::attn_fwd_kernel<__half, 0, true>);
   } else if (dtype == kDtypeBF16) {

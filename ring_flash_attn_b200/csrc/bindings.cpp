@@ -82,11 +82,13 @@ void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, co
 
 void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
                    const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
-                   const FusedCtx* fc, const at::Tensor* seg_lo = nullptr) {
+                   const FusedCtx* fc, const at::Tensor* seg_lo = nullptr, const at::Tensor* scale_qk = nullptr,
+                   const at::Tensor* scale_v = nullptr) {
   const c10::cuda::CUDAGuard guard(q.device());
+  const bool fp8 = scale_qk != nullptr;
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(segs.scalar_type() == at::kInt && segs.is_cuda() && segs.is_contiguous() && segs.size(1) == 4);
-  TORCH_CHECK(out.is_contiguous() && out.scalar_type() == q.scalar_type());
+  TORCH_CHECK(out.is_contiguous() && out.scalar_type() == (fp8 ? at::kBFloat16 : q.scalar_type()));
   TORCH_CHECK(lse.is_contiguous() && lse.scalar_type() == at::kFloat);
   TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type());
   TORCH_CHECK(q.size(1) % k.size(1) == 0, "query heads must be a multiple of kv heads");
@@ -97,6 +99,20 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
     TORCH_CHECK(seg_lo->scalar_type() == at::kInt && seg_lo->is_cuda() && seg_lo->is_contiguous() &&
                 seg_lo->numel() == segs.size(0), "seg_lo must hold one int32 per segment");
     p.seg_lo = seg_lo->data_ptr<int>();
+  }
+  int dtype = 0;
+  if (fp8) {
+    TORCH_CHECK(q.scalar_type() == at::kFloat8_e4m3fn, "the fp8 forward takes float8_e4m3fn q / k / v");
+    TORCH_CHECK(fc == nullptr, "the fp8 forward is not wired into the fused multi-GPU launch yet");
+    TORCH_CHECK(scale_qk->scalar_type() == at::kFloat && scale_qk->is_cuda() && scale_qk->is_contiguous() &&
+                scale_qk->numel() == q.size(1), "head_scale_qk: one fp32 per query head");
+    TORCH_CHECK(scale_v->scalar_type() == at::kFloat && scale_v->is_cuda() && scale_v->is_contiguous() &&
+                scale_v->numel() == k.size(1), "head_scale_v: one fp32 per kv head");
+    p.head_scale_qk = scale_qk->data_ptr<float>();
+    p.head_scale_v = scale_v->data_ptr<float>();
+    dtype = rfa::kDtypeE4M3;
+  } else {
+    dtype = dtype_code(q);
   }
   p.out = out.data_ptr();
   p.lse = lse.data_ptr<float>();
@@ -111,11 +127,11 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
     fill_push(p.push, p.sig, *fc, k, v);
-    check(rfa::attn_fwd_launch(dtype_code(q), view3(q, "q"), view3(k, "k"), view3(v, "v"),
+    check(rfa::attn_fwd_launch(dtype, view3(q, "q"), view3(k, "k"), view3(v, "v"),
                                view3(fc->k_stage, "k_stage"), view3(fc->v_stage, "v_stage"), p,
                                at::cuda::getCurrentCUDAStream()));
   } else {
-    check(rfa::attn_fwd_launch(dtype_code(q), view3(q, "q"), view3(k, "k"), view3(v, "v"), view3(k, "k"),
+    check(rfa::attn_fwd_launch(dtype, view3(q, "q"), view3(k, "k"), view3(v, "v"), view3(k, "k"),
                                view3(v, "v"), p, at::cuda::getCurrentCUDAStream()));
   }
 }
@@ -127,6 +143,14 @@ void set_trace(const c10::optional<at::Tensor>& t) { g_trace = t.has_value() ? *
 void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
               const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale) {
   attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr);
+}
+
+// Experimental fp8 forward: q / k / v float8_e4m3fn (rows, heads, 128), out bf16.  head_scale_qk[h] = q_descale *
+// k_descale of query head h, head_scale_v[hk] = v_descale of kv head hk.
+void attn_fwd_fp8(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+                  const at::Tensor& segs, const at::Tensor& head_scale_qk, const at::Tensor& head_scale_v,
+                  at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale) {
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr, nullptr, &head_scale_qk, &head_scale_v);
 }
 
 // Sliding-window launch: seg_lo[i] is the lower band offset of segment i (see FwdParams::seg_lo).
@@ -373,6 +397,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_trace", &set_trace);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_window", &attn_fwd_window);
+  m.def("attn_fwd_fp8", &attn_fwd_fp8);
   m.def("attn_bwd_window", &attn_bwd_window);
   m.def("attn_fwd_fused", &attn_fwd_fused);
   m.def("attn_fwd_fused_window", &attn_fwd_fused_window);

@@ -6,6 +6,8 @@ steady state of a training loop performs no host work beyond the launches.
 """
 from __future__ import annotations
 
+import contextlib
+import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -24,6 +26,36 @@ def supported(q: torch.Tensor, k: torch.Tensor) -> bool:
 
 def _diag(d: Optional[int]) -> int:
     return DIAG_FULL if d is None else int(d)
+
+
+# ---- experimental fp8 forward (RFA_B200_FP8_KERNEL=1) --------------------------------------------------
+# The per-head descales of the running call; set by parallel/api.py around the engine call so that the
+# executors (which only know q / k / v) can hand them to the launch.
+_FP8_STATE = threading.local()
+
+
+@contextlib.contextmanager
+def fp8_scales(head_scale_qk: torch.Tensor, head_scale_v: torch.Tensor):
+    """head_scale_qk: (Hq,) fp32 = q_descale * k_descale per query head; head_scale_v: (Hkv,) fp32."""
+    prev = getattr(_FP8_STATE, "scales", None)
+    _FP8_STATE.scales = (head_scale_qk, head_scale_v)
+    try:
+        yield
+    finally:
+        _FP8_STATE.scales = prev
+
+
+def current_fp8_scales():
+    return getattr(_FP8_STATE, "scales", None)
+
+
+def is_fp8_kernel_input(q: torch.Tensor, k: torch.Tensor) -> bool:
+    return q.dtype == torch.float8_e4m3fn and k.dtype == torch.float8_e4m3fn and q.shape[-1] == 128
+
+
+def out_dtype(q: torch.Tensor) -> torch.dtype:
+    """fp8 inputs produce bf16 outputs."""
+    return torch.bfloat16 if q.element_size() == 1 else q.dtype
 
 
 LO_NONE = -(1 << 29)  # "no lower bound" in the sliding-window tables
@@ -290,13 +322,20 @@ def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None):
     C = cuda_ext.load()
     tq, hq, d = q.shape
     if out is None:
-        out = (torch.empty if covered else torch.zeros)((tq, hq, d), dtype=q.dtype, device=q.device)
+        out = (torch.empty if covered else torch.zeros)((tq, hq, d), dtype=out_dtype(q), device=q.device)
     if lse is None:
         lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
         if not covered:
             lse.fill_(float("-inf"))
     if items.shape[0]:
-        C.attn_fwd(_rows3(q), _rows3(k), _rows3(v), items, segs, out, lse, tq, float(scale))
+        if is_fp8_kernel_input(q, k):
+            scales = current_fp8_scales()
+            if scales is None:
+                raise RuntimeError("fp8 tensors reached the kernel launch without descales (attn_cuda.fp8_scales)")
+            C.attn_fwd_fp8(_rows3(q), _rows3(k), _rows3(v), items, segs, scales[0], scales[1], out, lse, tq,
+                           float(scale))
+        else:
+            C.attn_fwd(_rows3(q), _rows3(k), _rows3(v), items, segs, out, lse, tq, float(scale))
         cuda_ext.note_launch()
     return out, lse
 

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import functools
 import os
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -82,7 +82,14 @@ def _pad_head_dim(q) -> int:
     return 0
 
 
-def _cp_apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic):
+def _cp_apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic, fp8=None):
+    if fp8 is not None:
+        # experimental fp8 forward: e4m3 q / k / v straight into the kernels (and over the wire), bf16 out.
+        # Forward only - fp8 tensors carry no gradient.
+        from ..ops import attn_cuda
+
+        with attn_cuda.fp8_scales(*fp8), torch.no_grad():
+            return engine.cp_forward(plan, q, k, v, scale, group, transport, heads_k_stride)
     pad = _pad_head_dim(q)
     if pad:
         d = q.shape[-1]
@@ -98,16 +105,57 @@ except AttributeError:  # pragma: no cover - very old torch
     pass
 
 
-def _maybe_dequant(q, k, v, descale):
-    """fp8 extension (utils/fp8.py): ``descale`` is a tensor for a packed input or a (q, k, v) tuple."""
+def _per_head(descale, x) -> Optional[torch.Tensor]:
+    """(H,) fp32 vector if ``descale`` is a per-tensor or per-head scale of ``x`` (heads at dim -2), else None."""
+    heads = x.shape[-2]
+    if descale is None:
+        return torch.ones(heads, dtype=torch.float32, device=x.device)
+    if not isinstance(descale, torch.Tensor):
+        return torch.full((heads,), float(descale), dtype=torch.float32, device=x.device)
+    if descale.numel() == 1:
+        return descale.reshape(1).to(device=x.device, dtype=torch.float32).expand(heads).contiguous()
+    if descale.dim() == x.dim() and descale.shape[-2] == heads and descale.numel() == heads:
+        return descale.reshape(heads).to(device=x.device, dtype=torch.float32).contiguous()
+    return None
+
+
+def _fp8_kernel_scales(q, k, v, dq, dk, dv, window_size):
+    """Descales for the experimental fp8 forward kernel, or None when the call does not qualify: opt-in
+    (``RFA_B200_FP8_KERNEL=1``), e4m3 q/k/v with head_dim 128 on a Blackwell GPU, per-tensor or per-head
+    descales, no sliding window.  Finer block scales take the dequantise-to-bf16 path."""
+    if os.environ.get("RFA_B200_FP8_KERNEL", "0") != "1":
+        return None
+    if not (q.dtype == k.dtype == v.dtype == torch.float8_e4m3fn) or q.shape[-1] != 128 or not q.is_cuda:
+        return None
+    if tuple(window_size) != (-1, -1):
+        return None
+    from ..ops import cuda_ext
+
+    if not cuda_ext.available_for(q):
+        return None
+    sq, sk, sv = _per_head(dq, q), _per_head(dk, k), _per_head(dv, v)
+    if sq is None or sk is None or sv is None:
+        return None
+    rep = q.shape[-2] // k.shape[-2]
+    return (sq * sk.repeat_interleave(rep)).contiguous(), sv
+
+
+def _maybe_dequant(q, k, v, descale, window_size=(-1, -1)):
+    """fp8 extension (utils/fp8.py): ``descale`` is a tensor for a packed input or a (q, k, v) tuple.
+
+    Returns (q, k, v, fp8_scales): either dequantised tensors and None, or - for calls that qualify for the
+    experimental fp8 kernel - the untouched e4m3 tensors and their per-head descales."""
     from ..utils import fp8
 
     if not (fp8.is_fp8(q) or fp8.is_fp8(k) or fp8.is_fp8(v)):
-        return q, k, v
+        return q, k, v, None
     if descale is None:
         raise ValueError("fp8 q/k/v need descale=(q_descale, k_descale, v_descale)")
     dq, dk, dv = descale if isinstance(descale, (tuple, list)) else (descale, descale, descale)
-    return fp8.dequantize(q, dq), fp8.dequantize(k, dk), fp8.dequantize(v, dv)
+    scales = _fp8_kernel_scales(q, k, v, dq, dk, dv, window_size)
+    if scales is not None:
+        return q, k, v, scales
+    return fp8.dequantize(q, dq), fp8.dequantize(k, dk), fp8.dequantize(v, dv), None
 
 
 def _split_descale(descale, pack_dim: int, n: int):
@@ -193,7 +241,7 @@ def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=Non
 def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
                deterministic, return_attn_probs, group, descale=None):
     _check_common(q, dropout_p, window_size, alibi_slopes)
-    q, k, v = _maybe_dequant(q, k, v, descale)
+    q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
     if scheme in ("zigzag", "stripe") and not causal:
         raise AssertionError(f"{scheme} attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
@@ -203,7 +251,7 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
     plan.peer = lambda r, _a=(scheme, world, b, s, bool(causal), win): _batch_plan(_a[0], r, *_a[1:])
     out, lse = _cp_apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
                                  v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
-                                 "ring", 1, deterministic)
+                                 "ring", 1, deterministic, fp8)
     out = out.view(b, s, hq, d)
     if not return_attn_probs:
         return out
@@ -213,7 +261,7 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
 def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scale, causal, window_size,
                 alibi_slopes, deterministic, return_attn_probs, group, descale=None):
     _check_common(q, dropout_p, window_size, alibi_slopes)
-    q, k, v = _maybe_dequant(q, k, v, descale)
+    q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
     if scheme == "zigzag" and not causal:
         raise AssertionError("zigzag attention only supports causal=True (as in the reference)")
     rank, world = group_info(group)
@@ -223,7 +271,7 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
     plan.peer = lambda r, _a=(scheme, world, cu_host, bool(causal), win): _varlen_plan(_a[0], r, *_a[1:])
     if plan.q_rows != q.shape[0]:
         raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
-    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic)
+    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic, fp8)
     return (out, lse, None) if return_attn_probs else out
 
 
@@ -367,7 +415,7 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
     """llama3-style CP: q/k/v (T_local, H*, D) are a contiguous slice of the flat token stream; the
     cu_seqlens / local_k_slice come from :func:`llama3_flash_attn_prepare_cu_seqlens`."""
     _check_common(q, dropout_p, window_size, alibi_slopes)
-    q, k, v = _maybe_dequant(q, k, v, descale)
+    q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
     rank, world = group_info(group)
     k_start = local_k_slice.start or 0
     cu_q_host, cu_k_host = cu_seqlens_to_host(cu_seqlens_q), cu_seqlens_to_host(cu_seqlens_k)
@@ -385,7 +433,7 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
         # locally, so this call uses the torch.distributed all-gather transport around the same kernels
         plan.fused_ok = False
     out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
-                                 int(heads_k_stride), deterministic)
+                                 int(heads_k_stride), deterministic, fp8)
     return (out, lse, None) if return_attn_probs else out
 
 

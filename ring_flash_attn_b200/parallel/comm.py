@@ -12,6 +12,12 @@ import torch
 import torch.distributed as dist
 
 
+def _wire(t: torch.Tensor) -> torch.Tensor:
+    """One-byte float tensors (fp8 K/V of the experimental fp8 forward) travel as uint8: same bytes, and every
+    backend knows the type."""
+    return t.view(torch.uint8) if t.element_size() == 1 and t.dtype != torch.uint8 else t
+
+
 def group_info(group: Optional[dist.ProcessGroup]):
     """(rank, world) of ``group``; (0, 1) when torch.distributed is not initialised."""
     if not (dist.is_available() and dist.is_initialized()):
@@ -43,8 +49,8 @@ class RingComm:
         if self.world == 1:
             out.copy_(to_send)
             return out
-        self._queued.append(dist.P2POp(dist.isend, to_send, self.send_rank, group=self.group))
-        self._queued.append(dist.P2POp(dist.irecv, out, self.recv_rank, group=self.group))
+        self._queued.append(dist.P2POp(dist.isend, _wire(to_send), self.send_rank, group=self.group))
+        self._queued.append(dist.P2POp(dist.irecv, _wire(out), self.recv_rank, group=self.group))
         return out
 
     def commit(self) -> None:
@@ -78,7 +84,7 @@ class AllGatherComm:
         if self.world == 1:
             output.copy_(inp.reshape(output.shape))
             return
-        self._handles.append(dist.all_gather_into_tensor(output, inp, group=self.group, async_op=True))
+        self._handles.append(dist.all_gather_into_tensor(_wire(output), _wire(inp), group=self.group, async_op=True))
 
     def wait(self) -> None:
         for h in self._handles:

@@ -42,6 +42,8 @@ def _use_cuda_kernels(q: torch.Tensor, k: Optional[torch.Tensor] = None) -> bool
 
     if not cuda_ext.available_for(q):
         return False
+    if attn_cuda.is_fp8_kernel_input(q, q if k is None else k):
+        return attn_cuda.current_fp8_scales() is not None  # experimental fp8 forward (parallel/api.py)
     return attn_cuda.supported(q, q if k is None else k)
 
 
@@ -129,11 +131,15 @@ def step_backward(plan: CPPlan, segs: List[Segment], dout, q, k_src, v_src, lse,
     return dk, dv
 
 
+def _out_dtype(q: torch.Tensor) -> torch.dtype:
+    return torch.bfloat16 if q.element_size() == 1 else q.dtype  # fp8 inputs produce bf16 outputs
+
+
 def _finish_forward(q, out, lse):
     if out is None:  # nothing visible at all (cannot happen for valid plans, but stay total)
         out = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
         lse = torch.full((q.shape[1], q.shape[0]), float("-inf"), dtype=torch.float32, device=q.device)
-    return out.to(q.dtype), lse
+    return out.to(_out_dtype(q)), lse
 
 
 def compute_delta(out: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
@@ -193,6 +199,18 @@ def ring_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determini
 # all-gather transport (llama3 pattern: gather a group of kv heads, attend, reduce-scatter grads)
 # ----------------------------------------------------------------------------------------------
 
+def _head_group_scales(q_heads: slice, kv_heads: slice):
+    """fp8 forward: a launch over a group of heads indexes its descales by LOCAL head."""
+    from ..ops import attn_cuda
+
+    scales = attn_cuda.current_fp8_scales()
+    if scales is None:
+        import contextlib
+
+        return contextlib.nullcontext()
+    return attn_cuda.fp8_scales(scales[0][q_heads].contiguous(), scales[1][kv_heads].contiguous())
+
+
 def _head_groups(hkv: int, stride: int):
     if hkv % stride:
         raise ValueError(f"heads_k_stride={stride} must divide the number of kv heads ({hkv})")
@@ -211,7 +229,7 @@ def allgather_forward(plan: CPPlan, q, k, v, scale, group, heads_k_stride: int):
     comm = AllGatherComm(group)
     by_src = plan.by_src()
     bufs = [torch.empty((2, W * L, heads_k_stride, d), dtype=k.dtype, device=k.device) for _ in range(2)]
-    out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    out = torch.empty(q.shape, dtype=_out_dtype(q), device=q.device)
     lse = torch.empty((hq, q.shape[0]), dtype=torch.float32, device=q.device)
     groups = list(_head_groups(hkv, heads_k_stride))
     _gather_heads(comm, k, v, groups[0], heads_k_stride, bufs[0])
@@ -223,9 +241,10 @@ def allgather_forward(plan: CPPlan, q, k, v, scale, group, heads_k_stride: int):
         qs = slice(h0 * rep, (h0 + heads_k_stride) * rep)
         q_g = q[:, qs]
         o_g = l_g = None
-        for src in range(W):
-            o_g, l_g = step_forward(plan, by_src.get(src, []), q_g, cur[0, src * L:(src + 1) * L],
-                                    cur[1, src * L:(src + 1) * L], scale, o_g, l_g)
+        with _head_group_scales(qs, slice(h0, h0 + heads_k_stride)):
+            for src in range(W):
+                o_g, l_g = step_forward(plan, by_src.get(src, []), q_g, cur[0, src * L:(src + 1) * L],
+                                        cur[1, src * L:(src + 1) * L], scale, o_g, l_g)
         o_g, l_g = _finish_forward(q_g, o_g, l_g)
         out[:, qs] = o_g
         lse[qs] = l_g
@@ -277,7 +296,7 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 # ----------------------------------------------------------------------------------------------
 
 def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
-    if not _use_cuda_kernels(q, k):
+    if not _use_cuda_kernels(q, k) or q.element_size() == 1:  # the fp8 forward is not in the fused launch yet
         return False
     if plan is not None and (not getattr(plan, "fused_ok", True) or not _kernels_take(plan)):
         return False

@@ -64,3 +64,27 @@ def test_kvpacked_and_unpacked_fp8_share_semantics():
     torch.testing.assert_close(a, b)
     with pytest.raises(ValueError):
         rfa.ring_flash_attn_kvpacked_func(q8, kv8, causal=True)
+
+
+def test_fp8_kernel_opt_in_is_ignored_off_gpu(monkeypatch):
+    """RFA_B200_FP8_KERNEL=1 only changes calls that can run on the kernels; CPU tensors keep the dequantise path."""
+    import ring_flash_attn_b200 as rfa
+    from ring_flash_attn_b200.ops.dense import attention_oracle
+    from ring_flash_attn_b200.parallel import api
+    from ring_flash_attn_b200.utils import fp8
+
+    monkeypatch.setenv("RFA_B200_FP8_KERNEL", "1")
+    torch.manual_seed(0)
+    qkv = torch.randn(1, 64, 3, 2, 128)
+    q8, d = fp8.quantize_blockwise(qkv, [0, 0, 1, 1, 0])
+    deq = fp8.dequantize(q8, d, torch.float32)
+    ref, _ = attention_oracle(deq[:, :, 0], deq[:, :, 1], deq[:, :, 2], True)
+    out = rfa.ring_flash_attn_qkvpacked_func(q8, causal=True, descale=d)
+    torch.testing.assert_close(out.float(), ref, atol=3e-2, rtol=3e-2)
+    # per-head reduction of descales (what the kernel path consumes)
+    x = torch.zeros(1, 8, 4, 128)
+    assert api._per_head(None, x).tolist() == [1.0] * 4
+    assert api._per_head(0.5, x).tolist() == [0.5] * 4
+    assert api._per_head(torch.tensor(2.0), x).tolist() == [2.0] * 4
+    assert api._per_head(torch.arange(4.0).view(1, 1, 4, 1), x).tolist() == [0.0, 1.0, 2.0, 3.0]
+    assert api._per_head(torch.ones(1, 2, 4, 1), x) is None  # token-block scales: not per-head

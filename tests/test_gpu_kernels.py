@@ -235,3 +235,46 @@ def test_sliding_window_kernels(monkeypatch, fn_name, causal, window):
     torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
     assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
     assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
+
+
+@_EXPERIMENTAL
+def test_fp8_descriptor_probe():
+    """kind::f8f6f4 operand forms of the fp8 forward (benchmark/probe_fp8.py sweeps alternatives on a mismatch)."""
+    C = _ext()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = (torch.randn(128, 128, device="cuda", generator=g) * 0.5).to(torch.float8_e4m3fn)
+    b = (torch.randn(128, 128, device="cuda", generator=g) * 0.5).to(torch.float8_e4m3fn)
+    for a_kind, b_kind, ref in ((0, 0, a.float() @ b.float().t()), (1, 1, a.float() @ b.float())):
+        out = C.probe_fp8(a, b, [a_kind, b_kind, 0, -1, -1, -1])
+        torch.cuda.synchronize()
+        assert (out - ref).abs().max().item() < 1e-3 * max(ref.abs().max().item(), 1.0), (a_kind, b_kind)
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("per_head", [False, True])
+def test_fp8_forward_kernel(monkeypatch, per_head):
+    """RFA_B200_FP8_KERNEL=1: e4m3 q/k/v go straight into the forward kernel (kind::f8f6f4 for both GEMMs, P as
+    e4m3 in tensor memory); compared with the oracle on the dequantised tensors at fp8 tolerance."""
+    from ring_flash_attn_b200.ops import cuda_ext
+    from ring_flash_attn_b200.utils import fp8
+
+    monkeypatch.setenv("RFA_B200_FP8_KERNEL", "1")
+    torch.manual_seed(0)
+    q = torch.randn(1, 900, 8, 128, device="cuda") * 1.5
+    kv = torch.randn(1, 900, 2, 2, 128, device="cuda") * 1.5
+    if per_head:
+        q8, dq = fp8.quantize_blockwise(q, [0, 0, 1, 0])
+        kv8, dkv = fp8.quantize_blockwise(kv, [0, 0, 1, 1, 0])
+    else:
+        q8, dq = fp8.quantize_blockwise(q, [0, 0, 0, 0])
+        kv8, dkv = fp8.quantize_blockwise(kv, [0, 0, 1, 0, 0])
+    qd = fp8.dequantize(q8, dq, torch.float32)
+    kvd = fp8.dequantize(kv8, dkv, torch.float32)
+    ref, ref_lse = attention_oracle(qd, kvd[:, :, 0], kvd[:, :, 1], True)
+    before = cuda_ext.launch_counter().value
+    out, lse, _ = rfa.zigzag_ring_flash_attn_kvpacked_func(q8, kv8, causal=True, descale=(dq, dkv),
+                                                           return_attn_probs=True)
+    assert cuda_ext.launch_counter().value == before + 1 and out.dtype == torch.bfloat16
+    torch.testing.assert_close(lse, ref_lse, atol=2e-2, rtol=2e-2)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-2 * ref.abs().max().item() + 2e-2, err
