@@ -103,7 +103,6 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   int dtype = 0;
   if (fp8) {
     TORCH_CHECK(q.scalar_type() == at::kFloat8_e4m3fn, "the fp8 forward takes float8_e4m3fn q / k / v");
-    TORCH_CHECK(fc == nullptr, "the fp8 forward is not wired into the fused multi-GPU launch yet");
     TORCH_CHECK(scale_qk->scalar_type() == at::kFloat && scale_qk->is_cuda() && scale_qk->is_contiguous() &&
                 scale_qk->numel() == q.size(1), "head_scale_qk: one fp32 per query head");
     TORCH_CHECK(scale_v->scalar_type() == at::kFloat && scale_v->is_cuda() && scale_v->is_contiguous() &&
@@ -151,6 +150,13 @@ void attn_fwd_fp8(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                   const at::Tensor& segs, const at::Tensor& head_scale_qk, const at::Tensor& head_scale_v,
                   at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale) {
   attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr, nullptr, &head_scale_qk, &head_scale_v);
+}
+
+// The same inside the fused multi-GPU launch (K/V rows travel as one byte per element).
+void attn_fwd_fused_fp8(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
+                        const at::Tensor& segs, const at::Tensor& head_scale_qk, const at::Tensor& head_scale_v,
+                        at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale, const FusedCtx& fc) {
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, &fc, nullptr, &head_scale_qk, &head_scale_v);
 }
 
 // Sliding-window launch: seg_lo[i] is the lower band offset of segment i (see FwdParams::seg_lo).
@@ -398,6 +404,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_window", &attn_fwd_window);
   m.def("attn_fwd_fp8", &attn_fwd_fp8);
+  m.def("attn_fwd_fused_fp8", &attn_fwd_fused_fp8);
   m.def("attn_bwd_window", &attn_bwd_window);
   m.def("attn_fwd_fused", &attn_fwd_fused);
   m.def("attn_fwd_fused_window", &attn_fwd_fused_window);

@@ -296,8 +296,10 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 # ----------------------------------------------------------------------------------------------
 
 def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
-    if not _use_cuda_kernels(q, k) or q.element_size() == 1:  # the fp8 forward is not in the fused launch yet
+    if not _use_cuda_kernels(q, k):
         return False
+    if q.element_size() == 1 and os.environ.get("RFA_B200_FP8_KERNEL", "0") != "2":
+        return False  # fp8 forward inside the fused launch: second opt-in level (=2), validated after level 1
     if plan is not None and (not getattr(plan, "fused_ok", True) or not _kernels_take(plan)):
         return False
     from . import fused

@@ -32,17 +32,22 @@ def available(q: torch.Tensor, group) -> bool:
 # ----------------------------------------------------------------------------------------------
 
 def _forward_local(plan: CPPlan, q, k, v, scale):
+    if attn_cuda.has_window(plan.segments):  # kWindow kernel variant with per-item trimmed tables
+        return attn_cuda.segments_forward(plan, plan.segments, q, k, v, scale)
     items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
     return attn_cuda.forward_launch(q, k, v, items, segs, covered, scale)
 
 
 def _backward_local(plan: CPPlan, dout, q, k, v, out, lse, scale):
-    items, qsegs = attn_cuda.bwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
     delta = attn_cuda.compute_delta(out, dout)
     dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
     dk = torch.zeros(k.shape, dtype=torch.float32, device=q.device)
     dv = torch.zeros(v.shape, dtype=torch.float32, device=q.device)
-    attn_cuda.backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq, dk, dv)
+    if attn_cuda.has_window(plan.segments):
+        attn_cuda.segments_backward(plan, plan.segments, dout, q, k, v, lse, delta, scale, dq, dk, dv)
+    else:
+        items, qsegs = attn_cuda.bwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
+        attn_cuda.backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq, dk, dv)
     return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
 
 

@@ -274,11 +274,14 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
         items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, offsets, q.device, ("fused",), flags)
     fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hq)
     tq = q.shape[0]
-    out = (torch.empty if covered else torch.zeros)((tq, hq, 128), dtype=q.dtype, device=q.device)
+    out = (torch.empty if covered else torch.zeros)((tq, hq, 128), dtype=attn_cuda.out_dtype(q), device=q.device)
     lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
     if not covered:
         lse.fill_(float("-inf"))
-    if window:
+    if attn_cuda.is_fp8_kernel_input(q, k):
+        sq, sv = attn_cuda.current_fp8_scales()
+        C.attn_fwd_fused_fp8(attn_cuda._rows3(q), k, v, items, segs, sq, sv, out, lse, tq, float(scale), fc)
+    elif window:
         C.attn_fwd_fused_window(attn_cuda._rows3(q), k, v, items, segs, seg_lo, out, lse, tq, float(scale), fc)
     else:
         C.attn_fwd_fused(attn_cuda._rows3(q), k, v, items, segs, out, lse, tq, float(scale), fc)
