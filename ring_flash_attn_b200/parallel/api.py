@@ -74,7 +74,7 @@ def _pad_head_dim(q) -> int:
         return 0
     if mode == "force":
         return KERNEL_HEAD_DIM - d
-    if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16):
+    if q.dtype in (torch.bfloat16, torch.float16):
         from ..ops import cuda_ext
 
         if cuda_ext.available_for(q):
@@ -125,7 +125,7 @@ def _fp8_kernel_scales(q, k, v, dq, dk, dv, window_size):
     descales, no sliding window.  Finer block scales take the dequantise-to-bf16 path."""
     if os.environ.get("RFA_B200_FP8_KERNEL", "0") != "1":
         return None
-    if not (q.dtype == k.dtype == v.dtype == torch.float8_e4m3fn) or q.shape[-1] != 128 or not q.is_cuda:
+    if not (q.dtype == k.dtype == v.dtype == torch.float8_e4m3fn) or q.shape[-1] != 128:
         return None
     if tuple(window_size) != (-1, -1):
         return None

@@ -36,11 +36,9 @@ def _use_cuda_kernels(q: torch.Tensor, k: Optional[torch.Tensor] = None) -> bool
     """True when the sm_100a kernels handle this call (Blackwell GPU, bf16/fp16, head_dim 128).
 
     Other CUDA inputs (e.g. head_dim 64) run the dense torch blocks on the GPU - slow but correct."""
-    if not q.is_cuda:
-        return False
     from ..ops import attn_cuda, cuda_ext
 
-    if not cuda_ext.available_for(q):
+    if not cuda_ext.available_for(q):  # False for anything that is not a Blackwell GPU tensor
         return False
     if attn_cuda.is_fp8_kernel_input(q, q if k is None else k):
         return attn_cuda.current_fp8_scales() is not None  # experimental fp8 forward (parallel/api.py)

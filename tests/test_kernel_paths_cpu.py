@@ -1,0 +1,126 @@
+"""The code paths that normally need a B200 - work tables, launch dispatch (plain / sliding window / fp8), per-source
+ring steps, autograd bridge - run on CPU against the dense oracle, with the extension replaced by
+``tests/fake_ext.py`` (a torch implementation of each launch's contract, driven by the same tables)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+import ring_flash_attn_b200 as rfa
+from ring_flash_attn_b200.ops.dense import attention_oracle, varlen_attention_oracle
+from ring_flash_attn_b200.parallel import layouts
+from dist_utils import run_distributed
+
+BF16 = dict(atol=3e-2, rtol=3e-2)
+
+
+def _grad_close(got, want):
+    assert (got.float() - want).abs().max().item() < 5e-2 * want.abs().max().item() + 2e-2
+
+
+def _case(rank, world, window, expect):
+    import fake_ext
+
+    os.environ["RFA_B200_DISABLE_P2P"] = "1"  # no CUDA IPC here: per-source launches around the ring transport
+    fake = fake_ext.install()
+    torch.manual_seed(0)
+    S, H, HK, d = 320 * world, 4, 2, 128
+    q = torch.randn(1, S, H, d).to(torch.bfloat16)
+    kv = torch.randn(1, S, 2, HK, d).to(torch.bfloat16)
+    dout = torch.randn(1, S, H, d).to(torch.bfloat16)
+    if world > 1:
+        for t in (q, kv, dout):
+            dist.broadcast(t, src=0)
+    rq, rkv = q.float().requires_grad_(True), kv.float().requires_grad_(True)
+    for scheme, prefix in (("ring", "ring"), ("zigzag", "zigzag_ring"), ("stripe", "stripe")):
+        rq.grad = rkv.grad = None
+        ref, ref_lse = attention_oracle(rq, rkv[:, :, 0], rkv[:, :, 1], True, window_size=window)
+        ref.backward(dout.float())
+        shard = getattr(layouts, f"shard_{scheme}")
+        lq = shard(q, rank, world).detach().requires_grad_(True)
+        lkv = shard(kv, rank, world).detach().requires_grad_(True)
+        fake.calls.clear()
+        out, lse, _ = getattr(rfa, f"{prefix}_flash_attn_kvpacked_func")(lq, lkv, causal=True, window_size=window,
+                                                                      return_attn_probs=True)
+        out.backward(shard(dout, rank, world))
+        assert set(expect) <= set(fake.calls), (scheme, fake.calls)
+        torch.testing.assert_close(out.float(), shard(ref, rank, world), **BF16)
+        torch.testing.assert_close(lse, shard(ref_lse, rank, world, dim=2), atol=2e-3, rtol=2e-3)
+        _grad_close(lq.grad, shard(rq.grad, rank, world))
+        _grad_close(lkv.grad, shard(rkv.grad, rank, world))
+    # packed documents (varlen) through the same launches
+    cu = [0, 96 * world, 224 * world, S]
+    cu_t = torch.tensor(cu, dtype=torch.int32)
+    q2, k2, v2 = q[0], kv[0, :, 0], kv[0, :, 1]
+    r2 = [t.float().requires_grad_(True) for t in (q2, k2, v2)]
+    ref, _ = varlen_attention_oracle(*r2, cu_t, True, window_size=window)
+    ref.backward(dout[0].float())
+    sh = lambda x: layouts.shard_zigzag_varlen(x, cu, rank, world)  # noqa: E731
+    l2 = [sh(t).detach().requires_grad_(True) for t in (q2, k2, v2)]
+    local_cu = cu_t // world
+    out = rfa.zigzag_ring_flash_attn_varlen_func(*l2, local_cu, int((local_cu[1:] - local_cu[:-1]).max()), causal=True,
+                                                 window_size=window)
+    out.backward(sh(dout[0]))
+    torch.testing.assert_close(out.float(), sh(ref), **BF16)
+    for g, r in zip(l2, r2):
+        _grad_close(g.grad, sh(r.grad))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_plain_launch_path(world):
+    # the single-GPU path also launches the delta kernel; the ring transport computes delta with torch
+    run_distributed(_case, world, (-1, -1), ("attn_fwd", "attn_bwd") + (("attn_bwd_delta",) if world == 1 else ()))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("window", [(70, 0), (250, 0)])
+def test_window_launch_path(world, window, monkeypatch):
+    monkeypatch.setenv("RFA_B200_WINDOW_KERNEL", "1")
+    run_distributed(_case, world, window, ("attn_fwd_window", "attn_bwd_window"))
+
+
+def _fp8_case(rank, world):
+    import fake_ext
+    from ring_flash_attn_b200.utils import fp8
+
+    os.environ["RFA_B200_DISABLE_P2P"] = "1"
+    os.environ["RFA_B200_FP8_KERNEL"] = "1"
+    fake = fake_ext.install()
+    torch.manual_seed(0)
+    S, H, HK, d = 256 * world, 4, 2, 128
+    q = torch.randn(1, S, H, d)
+    kv = torch.randn(1, S, 2, HK, d)
+    if world > 1:
+        dist.broadcast(q, src=0)
+        dist.broadcast(kv, src=0)
+    q8, dq = fp8.quantize_blockwise(q, [0, 0, 1, 0])  # per head
+    kv8, dkv = fp8.quantize_blockwise(kv, [0, 0, 1, 1, 0])
+    qd, kvd = fp8.dequantize(q8, dq, torch.float32), fp8.dequantize(kv8, dkv, torch.float32)
+    ref, ref_lse = attention_oracle(qd, kvd[:, :, 0], kvd[:, :, 1], True)
+    for scheme, fn in (("zigzag", rfa.zigzag_ring_flash_attn_kvpacked_func), ("ring", rfa.ring_flash_attn_kvpacked_func)):
+        shard = getattr(layouts, f"shard_{scheme}")
+        fake.calls.clear()
+        out, lse, _ = fn(shard(q8.view(torch.uint8), rank, world).view(torch.float8_e4m3fn),
+                         shard(kv8.view(torch.uint8), rank, world).view(torch.float8_e4m3fn), causal=True,
+                         descale=(dq, dkv), return_attn_probs=True)
+        assert fake.calls and set(fake.calls) == {"attn_fwd_fp8"}, fake.calls
+        assert out.dtype == torch.bfloat16
+        torch.testing.assert_close(out.float(), shard(ref, rank, world), **BF16)
+        torch.testing.assert_close(lse, shard(ref_lse, rank, world, dim=2), atol=2e-3, rtol=2e-3)
+    # llama3 entry point: the all-gather transport slices the descales per head group
+    cu = torch.tensor([0, S // 2 + 3, S], dtype=torch.int32)
+    refv, _ = varlen_attention_oracle(qd[0], kvd[0, :, 0], kvd[0, :, 1], cu, True)
+    cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu, True, rank, world)
+    sh = lambda x: layouts.shard_llama3(x, rank, world)  # noqa: E731
+    fake.calls.clear()
+    out = rfa.llama3_flash_attn_varlen_kvpacked_func(
+        sh(q8[0].view(torch.uint8)).view(torch.float8_e4m3fn), sh(kv8[0].view(torch.uint8)).view(torch.float8_e4m3fn),
+        cq, ck, mq, mk, heads_k_stride=1, local_k_slice=ks, causal=True, descale=(dq[0], dkv[0]))
+    assert set(fake.calls) == {"attn_fwd_fp8"}
+    torch.testing.assert_close(out.float(), sh(refv), **BF16)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_fp8_launch_path(world):
+    run_distributed(_fp8_case, world)
