@@ -202,6 +202,11 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
                             const TensorView& k_stage, const TensorView& v_stage, const FwdParams& p,
                             cudaStream_t stream);
 
+// 64-key-step variant of the forward (csrc/attn_fwd_h64_sm100.cu), same contract, bf16 / fp16 without windows.
+const char* attn_fwd_h64_launch(int dtype, const TensorView& q, const TensorView& k, const TensorView& v,
+                                const TensorView& k_stage, const TensorView& v_stage, const FwdParams& p,
+                                cudaStream_t stream);
+
 const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const TensorView& dout, float* delta, int lse_S,
                                   cudaStream_t stream);
 const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& dout, const TensorView& k,

@@ -122,16 +122,22 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
   p.n_items = static_cast<int>(items.size(0));
   p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
+  // opt-in forward variant with 64-key softmax steps (RFA_B200_FWD_H64=1), bf16 / fp16 without windows only
+  static const bool h64 = [] {
+    const char* e = std::getenv("RFA_B200_FWD_H64");
+    return e != nullptr && std::atoi(e) != 0;
+  }();
+  auto* launch_fwd = (h64 && !fp8 && seg_lo == nullptr) ? &rfa::attn_fwd_h64_launch : &rfa::attn_fwd_launch;
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
     fill_push(p.push, p.sig, *fc, k, v);
-    check(rfa::attn_fwd_launch(dtype, view3(q, "q"), view3(k, "k"), view3(v, "v"),
+    check(launch_fwd(dtype, view3(q, "q"), view3(k, "k"), view3(v, "v"),
                                view3(fc->k_stage, "k_stage"), view3(fc->v_stage, "v_stage"), p,
                                at::cuda::getCurrentCUDAStream()));
   } else {
-    check(rfa::attn_fwd_launch(dtype, view3(q, "q"), view3(k, "k"), view3(v, "v"), view3(k, "k"),
-                               view3(v, "v"), p, at::cuda::getCurrentCUDAStream()));
+    check(launch_fwd(dtype, view3(q, "q"), view3(k, "k"), view3(v, "v"), view3(k, "k"), view3(v, "v"), p,
+                     at::cuda::getCurrentCUDAStream()));
   }
 }
 

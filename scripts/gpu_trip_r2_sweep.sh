@@ -23,3 +23,8 @@ RFA_B200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_kernels
 echo "== fp8: kind::f8f6f4 descriptor probe (sweeps alternatives on a mismatch), then the fp8 forward kernel"
 timeout 300 python benchmark/probe_fp8.py > gpurun_out/probe_fp8.log 2>&1; echo "exit $?"; tail -4 gpurun_out/probe_fp8.log
 RFA_B200_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 500 -k "fp8" > gpurun_out/pytest_fp8.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_fp8.log
+echo "== forward variant with 64-key softmax steps (RFA_B200_FWD_H64=1): correctness, then speed vs the default"
+RFA_B200_FWD_H64=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "fwd_block or world1 or bwd_block" > gpurun_out/pytest_h64.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_h64.log
+for h in 0 1; do
+  RFA_B200_FWD_H64=$h timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_$h.log 2>&1; echo "h64=$h exit $?"; grep -i "fwd" gpurun_out/first_look_h64_$h.log | head -8
+done
