@@ -96,7 +96,7 @@ __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
   return g;
 }
 
-template <typename T, bool kWindow>
+template <typename T, bool kWindow, bool kDqDirect>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -579,6 +579,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&bars->dq_free);
+          if constexpr (kDqDirect) {
+            // thread == head-dim lane: for a fixed query row the 32 lanes of a warp hit 128 consecutive bytes, so
+            // every instruction is one coalesced L2 reduction - the same L2 traffic as the TMA reduce-add, without
+            // the 32 KB write + 32 KB read of the shared-memory staging tile
+            const int row0 = g.q_row0 + ti * kTileQ;
+            float* base = p.dq + static_cast<long long>(row0) * p.dq_row_stride + head * p.dq_head_stride + wg_tid;
+            const int n_ok = p.dq_rows - row0 < kTileQ ? p.dq_rows - row0 : kTileQ;  // clip at the tensor end
+#pragma unroll
+            for (int q = 0; q < kTileQ; ++q) {
+              if (q < n_ok)
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + q * p.dq_row_stride), "f"(__uint_as_float(r[q]))
+                             : "memory");
+            }
+            RFA_STAMP(wg_tid == 0, i, 12);
+            continue;
+          }
           // the previous tile's reduce must have finished reading the staging buffer
           if (wg_tid == 0) tma_store_wait_read<0>();
           named_bar_sync(4, 128);
@@ -669,12 +685,15 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
     if (err == cudaSuccess) kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   };
-  if (dtype == kDtypeBF16) {
-    if (p.window) launch(bwd::attn_bwd_kernel<__nv_bfloat16, true>);
-    else launch(bwd::attn_bwd_kernel<__nv_bfloat16, false>);
+  if (p.dq_direct && !p.window) {  // experimental dQ path (see BwdParams::dq_direct)
+    if (dtype == kDtypeBF16) launch(bwd::attn_bwd_kernel<__nv_bfloat16, false, true>);
+    else launch(bwd::attn_bwd_kernel<__half, false, true>);
+  } else if (dtype == kDtypeBF16) {
+    if (p.window) launch(bwd::attn_bwd_kernel<__nv_bfloat16, true, false>);
+    else launch(bwd::attn_bwd_kernel<__nv_bfloat16, false, false>);
   } else {
-    if (p.window) launch(bwd::attn_bwd_kernel<__half, true>);
-    else launch(bwd::attn_bwd_kernel<__half, false>);
+    if (p.window) launch(bwd::attn_bwd_kernel<__half, true, false>);
+    else launch(bwd::attn_bwd_kernel<__half, false, false>);
   }
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();

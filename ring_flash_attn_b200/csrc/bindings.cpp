@@ -222,6 +222,17 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
                  dq_accum.stride(1)};
   p.n_items = static_cast<int>(items.size(0));
   p.window = window ? 1 : 0;
+  {
+    static const int dq_direct = [] {
+      const char* e = std::getenv("RFA_B200_DQ_DIRECT");
+      return e ? std::atoi(e) : 0;
+    }();
+    p.dq_direct = dq_direct;
+    p.dq = dq_accum.data_ptr<float>();
+    p.dq_row_stride = dq_accum.stride(0);
+    p.dq_head_stride = dq_accum.stride(1);
+    p.dq_rows = static_cast<int>(dq_accum.size(0));
+  }
   if (const char* e = std::getenv("RFA_B200_DEBUG")) p.debug = std::atoi(e);
   p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
   if (fc != nullptr) {
