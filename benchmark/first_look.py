@@ -25,6 +25,8 @@ def timeit(fn, iters=20, warm=5):
 def main():
     res = {}
     try:
+        if os.environ.get("RFA_FIRST_LOOK_SKIP_FA2", "0") == "1":  # variant sweeps only need our side
+            raise ImportError("skipped")
         from flash_attn import flash_attn_func
     except Exception as e:  # noqa: BLE001
         flash_attn_func = None
@@ -72,7 +74,7 @@ def main():
         res[f"s{s}_hq{hq}_hkv{hkv}"] = row
         print(s, hq, hkv, json.dumps(row))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/first_look.json", "w") as f:
+    with open(os.environ.get("RFA_FIRST_LOOK_OUT", "gpurun_out/first_look.json"), "w") as f:
         json.dump(res, f, indent=1)
 
 

@@ -26,8 +26,8 @@ RFA_B200_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_kernels
 echo "== forward variant with 64-key softmax steps (RFA_B200_FWD_H64=1): correctness, then speed vs the default"
 RFA_B200_FWD_H64=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "fwd_block or world1 or bwd_block" > gpurun_out/pytest_h64.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_h64.log
 for h in 0 1; do
-  RFA_B200_FWD_H64=$h timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_$h.log 2>&1; echo "h64=$h exit $?"; grep -i "fwd" gpurun_out/first_look_h64_$h.log | head -8
+  RFA_B200_FWD_H64=$h RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_$h.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_$h.log 2>&1; echo "h64=$h exit $?"; grep -i "fwd" gpurun_out/first_look_h64_$h.log | head -8
 done
 echo "== backward variant: dQ^T added with coalesced red.global straight from registers (RFA_B200_DQ_DIRECT=1)"
 RFA_B200_DQ_DIRECT=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "bwd_block or world1" > gpurun_out/pytest_dqdirect.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_dqdirect.log
-RFA_B200_DQ_DIRECT=1 timeout 600 python benchmark/first_look.py > gpurun_out/first_look_dqdirect.log 2>&1; echo "exit $?"; grep -i "bwd" gpurun_out/first_look_dqdirect.log | head -8
+RFA_B200_DQ_DIRECT=1 RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_dqdirect.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_dqdirect.log 2>&1; echo "exit $?"; grep -i "bwd" gpurun_out/first_look_dqdirect.log | head -8
