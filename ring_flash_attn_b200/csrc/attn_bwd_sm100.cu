@@ -96,7 +96,10 @@ __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
   return g;
 }
 
-template <typename T, bool kWindow, bool kDqDirect>
+// kDsTmem (experimental, RFA_B200_BWD_V2 bit 1): dS^T is also parked in tensor memory (in the dP^T columns its
+// warpgroup has just consumed) and the dK GEMM takes it as a TMEM A-operand like dV takes P^T - one 16 KB
+// shared-memory operand read less per tile; the dQ^T GEMM still reads the shared-memory copy as its B operand.
+template <typename T, bool kWindow, bool kDqDirect, bool kDsTmem>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -291,11 +294,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           ph_ds ^= 1;
           tc_fence_after();
           RFA_STAMP(leader, i, 3);
-          if (leader)
+          if (leader) {
+            if constexpr (kDsTmem) {
 #pragma unroll
-          for (int k = 0; k < kTileQ / 16; ++k)
-            umma_ss2(tmem + kColDK, ds_km + k * (32 >> 4), hi, q_mn + k * (2048 >> 4), hi, idesc_dv,
-                     (i > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kTileQ / 16; ++k)
+                umma_ts2(tmem + kColDK, tmem + kColDP + (k >> 1) * 32 + (k & 1) * 8, q_mn + k * (2048 >> 4), hi,
+                         idesc_dv, (i > 0 || k > 0) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < kTileQ / 16; ++k)
+                umma_ss2(tmem + kColDK, ds_km + k * (32 >> 4), hi, q_mn + k * (2048 >> 4), hi, idesc_dv,
+                         (i > 0 || k > 0) ? 1u : 0u);
+            }
+          }
           if (i > 0) {  // previous dQ^T must have been drained out of TMEM
             mbar_wait(&bars->dq_free, ph_dqfree);
             ph_dqfree ^= 1;
@@ -460,6 +471,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld32(tmem + kColDP + lane_addr + c0, dpr);
           tmem_ld_wait();
           uint8_t* ds_row = smem_ds + key * 128;
+          [[maybe_unused]] uint32_t ds_pk[16];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             uint4 v;
@@ -470,9 +482,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               const float d0 = pr[c] * (__uint_as_float(dpr[c]) - dlt[c]) * p.scale;
               const float d1 = pr[c + 1] * (__uint_as_float(dpr[c + 1]) - dlt[c + 1]) * p.scale;
               w[e] = Pack2<T>::pack(d0, d1);
+              if constexpr (kDsTmem) ds_pk[ch * 4 + e] = w[e];
             }
             v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
             *reinterpret_cast<uint4*>(ds_row + (((half * 4 + ch) ^ (key & 7)) << 4)) = v;
+          }
+          if constexpr (kDsTmem) {
+            // the 32 dP^T columns of this warpgroup are in registers; their first 16 now hold its half of dS^T
+            tmem_st16(tmem + kColDP + lane_addr + c0, ds_pk);
+            tmem_st_wait();
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -685,15 +703,21 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
     if (err == cudaSuccess) kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   };
-  if (p.dq_direct && !p.window) {  // experimental dQ path (see BwdParams::dq_direct)
-    if (dtype == kDtypeBF16) launch(bwd::attn_bwd_kernel<__nv_bfloat16, false, true>);
-    else launch(bwd::attn_bwd_kernel<__half, false, true>);
-  } else if (dtype == kDtypeBF16) {
-    if (p.window) launch(bwd::attn_bwd_kernel<__nv_bfloat16, true, false>);
-    else launch(bwd::attn_bwd_kernel<__nv_bfloat16, false, false>);
+  const int v2 = p.window ? 0 : (p.dq_direct & 3);  // bit 0: direct dQ reduction, bit 1: dS^T as TMEM operand
+  if (dtype == kDtypeBF16) {
+    using B = __nv_bfloat16;
+    if (p.window) launch(bwd::attn_bwd_kernel<B, true, false, false>);
+    else if (v2 == 1) launch(bwd::attn_bwd_kernel<B, false, true, false>);
+    else if (v2 == 2) launch(bwd::attn_bwd_kernel<B, false, false, true>);
+    else if (v2 == 3) launch(bwd::attn_bwd_kernel<B, false, true, true>);
+    else launch(bwd::attn_bwd_kernel<B, false, false, false>);
   } else {
-    if (p.window) launch(bwd::attn_bwd_kernel<__half, true, false>);
-    else launch(bwd::attn_bwd_kernel<__half, false, false>);
+    using H = __half;
+    if (p.window) launch(bwd::attn_bwd_kernel<H, true, false, false>);
+    else if (v2 == 1) launch(bwd::attn_bwd_kernel<H, false, true, false>);
+    else if (v2 == 2) launch(bwd::attn_bwd_kernel<H, false, false, true>);
+    else if (v2 == 3) launch(bwd::attn_bwd_kernel<H, false, true, true>);
+    else launch(bwd::attn_bwd_kernel<H, false, false, false>);
   }
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();

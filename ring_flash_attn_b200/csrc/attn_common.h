@@ -176,8 +176,9 @@ struct BwdParams {
   int n_items;
   int debug;  // bisecting aid: bit1 = no S^T look-ahead
   int window;  // != 0: BwdQSegment::lo is meaningful (selects the kernel variant that masks the lower band edge)
-  // experimental (RFA_B200_DQ_DIRECT=1): the drain warpgroup adds dQ^T tiles to the accumulator with coalesced
-  // red.global.add.f32 straight from registers instead of staging them in shared memory for a TMA reduce-add
+  // experimental backward variants (RFA_B200_BWD_V2 bit mask).  Bit 0: the drain warpgroup adds dQ^T tiles to the
+  // accumulator with coalesced red.global.add.f32 straight from registers instead of staging them in shared memory
+  // for a TMA reduce-add.  Bit 1: dS^T is parked in tensor memory as the A operand of the dK GEMM.
   int dq_direct;
   float* dq;                 // the fp32 accumulator (rows, hq, 128) the TMA map tm_dq also points at
   long long dq_row_stride;   // floats

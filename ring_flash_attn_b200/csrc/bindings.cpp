@@ -224,7 +224,7 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
   p.window = window ? 1 : 0;
   {
     static const int dq_direct = [] {
-      const char* e = std::getenv("RFA_B200_DQ_DIRECT");
+      const char* e = std::getenv("RFA_B200_BWD_V2");  // bit 0: direct dQ reduction, bit 1: dS^T in TMEM
       return e ? std::atoi(e) : 0;
     }();
     p.dq_direct = dq_direct;

@@ -12,6 +12,8 @@ RFA_B200_FWD_H64=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu
 for h in 0 1; do
   RFA_B200_FWD_H64=$h RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_$h.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_$h.log 2>&1; echo "h64=$h exit $?"; grep -i "fwd" gpurun_out/first_look_h64_$h.log | head -8
 done
-echo "== backward variant: dQ^T added with coalesced red.global straight from registers (RFA_B200_DQ_DIRECT=1)"
-RFA_B200_DQ_DIRECT=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "bwd_block or world1" > gpurun_out/pytest_dqdirect.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_dqdirect.log
-RFA_B200_DQ_DIRECT=1 RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_dqdirect.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_dqdirect.log 2>&1; echo "exit $?"; grep -i "bwd" gpurun_out/first_look_dqdirect.log | head -8
+echo "== backward variants (RFA_B200_BWD_V2 bit 0: dQ^T via coalesced red.global from registers, bit 1: dS^T as TMEM operand of dK)"
+for v in 1 2 3; do
+  RFA_B200_BWD_V2=$v timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "bwd_block or world1" > gpurun_out/pytest_bwdv2_$v.log 2>&1; echo "v2=$v tests exit $?"; tail -3 gpurun_out/pytest_bwdv2_$v.log
+  RFA_B200_BWD_V2=$v RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_bwdv2_$v.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_bwdv2_$v.log 2>&1; echo "v2=$v bench exit $?"; grep -i "bwd" gpurun_out/first_look_bwdv2_$v.log | head -4
+done
