@@ -3,6 +3,12 @@
 The kernels (``csrc/attn_fwd_sm100.cu`` / ``attn_bwd_sm100.cu``) consume a :class:`CPPlan` as two small
 int32 tables.  Tables are cached on the plan object (plans themselves are lru-cached per shape), so the
 steady state of a training loop performs no host work beyond the launches.
+
+The launches stand where the reference calls flash-attn's private ops
+(``_flash_attn_forward`` / ``_flash_attn_backward`` and their varlen forms,
+/root/reference/ring_flash_attn/ring_flash_attn.py:53,131, ring_flash_attn_varlen.py:77,169,
+llama3_flash_attn_varlen.py:147,282); what the reference expresses as per-step slicing of q / k / v / lse
+(zigzag_ring_flash_attn.py:60-84, zigzag_ring_flash_attn_varlen.py:24-71) is a row of the work table here.
 """
 from __future__ import annotations
 

@@ -4,6 +4,10 @@
 ``world > 1`` : the same kernels, with every remote K/V shard arriving through peer-mapped staging
 buffers that the *attention kernel's own communication CTAs* fill over NVLink while the math on the
 local shard runs (``parallel/symm.py`` + ``csrc/comm_sm100.cu``).  No NCCL call is on this path.
+
+Replaces the per-step Python loops of the reference (flash-attn call + fp32 merge + batch_isend_irecv per ring
+step: /root/reference/ring_flash_attn/ring_flash_attn.py:7-154, zigzag_ring_flash_attn.py:7-199,
+stripe_flash_attn.py:7-231, and the all-gather / reduce-scatter loop of llama3_flash_attn_varlen.py:63-299).
 """
 from __future__ import annotations
 
