@@ -17,6 +17,9 @@
 #include <math_constants.h>
 #include <stdio.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "attn_common.h"
 #include "comm_device.cuh"
 #include "sm100_ptx.cuh"
@@ -76,7 +79,9 @@ __device__ __forceinline__ bool tile_needs_mask(const SegGeom& g, const WorkItem
   return ragged || diagonal;
 }
 
-template <typename T>
+// kPolyOf4: of every 4 element pairs of an unmasked step, this many take the polynomial exp2 on the FMA pipes
+// (RFA_B200_POLY_EXP, as in the default kernel; the 64-column steps leave the registers for it).
+template <typename T, int kPolyOf4>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_h64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_ks,
@@ -389,19 +394,32 @@ attn_fwd_h64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             turn_wait();
             const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2), nmc2 = pack2(-mc, -mc);
             uint64_t lsum = pack2(0.f, 0.f);
+            auto exp_chunks = [&](auto use_poly) {
 #pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-              uint32_t pk[16];
+              for (int c = 0; c < 64; c += 32) {
+                uint32_t pk[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint64_t x = ffma2(pack2(s[c + 2 * i], s[c + 2 * i + 1]), sc2, nmc2);
-                float x0, x1;
-                unpack2(x, x0, x1);
-                const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
-                lsum = fadd2(lsum, pack2(e0, e1));
-                pk[i] = Pack2<T>::pack(e0, e1);
+                for (int i = 0; i < 16; ++i) {
+                  const uint64_t x = ffma2(pack2(s[c + 2 * i], s[c + 2 * i + 1]), sc2, nmc2);
+                  float e0, e1;
+                  if (decltype(use_poly)::value && (i & 3) < kPolyOf4) {
+                    exp2_poly2(x, e0, e1);
+                  } else {
+                    float x0, x1;
+                    unpack2(x, x0, x1);
+                    e0 = fast_exp2(x0);
+                    e1 = fast_exp2(x1);
+                  }
+                  lsum = fadd2(lsum, pack2(e0, e1));
+                  pk[i] = Pack2<T>::pack(e0, e1);
+                }
+                tmem_st16(t_sh + (c >> 1), pk);  // P_h: 32 columns at the start of S_h
               }
-              tmem_st16(t_sh + (c >> 1), pk);  // P_h: 32 columns at the start of S_h
+            };
+            if (masked) {  // masked steps stay on MUFU so that masked entries are exact zeros
+              exp_chunks(std::false_type{});
+            } else {
+              exp_chunks(std::true_type{});
             }
             float l0, l1;
             unpack2(lsum, l0, l1);
@@ -480,8 +498,20 @@ const char* attn_fwd_h64_launch(int dtype, const TensorView& q, const TensorView
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd64::kSmemBytes);
     if (err == cudaSuccess) kern<<<grid, block, fwd64::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
   };
-  if (dtype == kDtypeBF16) launch(fwd64::attn_fwd_h64_kernel<__nv_bfloat16>);
-  else launch(fwd64::attn_fwd_h64_kernel<__half>);
+  static const int poly = [] {
+    const char* e = std::getenv("RFA_B200_POLY_EXP");
+    const int v = e ? std::atoi(e) : 0;
+    return v < 0 ? 0 : (v > 2 ? 2 : v);
+  }();
+  if (dtype == kDtypeBF16) {
+    if (poly == 0) launch(fwd64::attn_fwd_h64_kernel<__nv_bfloat16, 0>);
+    else if (poly == 1) launch(fwd64::attn_fwd_h64_kernel<__nv_bfloat16, 1>);
+    else launch(fwd64::attn_fwd_h64_kernel<__nv_bfloat16, 2>);
+  } else {
+    if (poly == 0) launch(fwd64::attn_fwd_h64_kernel<__half, 0>);
+    else if (poly == 1) launch(fwd64::attn_fwd_h64_kernel<__half, 1>);
+    else launch(fwd64::attn_fwd_h64_kernel<__half, 2>);
+  }
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

@@ -12,6 +12,9 @@ RFA_B200_FWD_H64=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu
 for h in 0 1; do
   RFA_B200_FWD_H64=$h RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_$h.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_$h.log 2>&1; echo "h64=$h exit $?"; grep -i "fwd" gpurun_out/first_look_h64_$h.log | head -8
 done
+for poly in 1 2; do
+  RFA_B200_FWD_H64=1 RFA_B200_POLY_EXP=$poly RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_poly$poly.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_poly$poly.log 2>&1; echo "h64 poly=$poly exit $?"; grep -i "fwd" gpurun_out/first_look_h64_poly$poly.log | head -4
+done
 echo "== backward variants (RFA_B200_BWD_V2 bit 0: dQ^T via coalesced red.global from registers, bit 1: dS^T as TMEM operand of dK)"
 for v in 1 2 3; do
   RFA_B200_BWD_V2=$v timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "bwd_block or world1" > gpurun_out/pytest_bwdv2_$v.log 2>&1; echo "v2=$v tests exit $?"; tail -3 gpurun_out/pytest_bwdv2_$v.log
