@@ -49,6 +49,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--forward-only", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="CPU/gloo dry run of the script itself (shapes / 64)")
+    ap.add_argument("--fp8-per-head", action="store_true",
+                    help="stripe8: per-head instead of per-128-token descales (the granularity the fp8 forward kernel "
+                         "takes natively with RFA_B200_FP8_KERNEL=1; finer scales are dequantised to bf16 first)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,7 +216,10 @@ def main():
             full = bcast(rnd(B, S, 3, H, d)) if world <= 8 else None
             local = layouts.shard_stripe(full, rank, world).contiguous()
             del full
-            q8, scale = fp8.quantize_blockwise(local, [1, 128 // min(shrink, 16), 1, 1, 0])  # per 128-token block and head
+            if args.fp8_per_head:
+                q8, scale = fp8.quantize_blockwise(local, [0, 0, 1, 1, 0])
+            else:
+                q8, scale = fp8.quantize_blockwise(local, [1, 128 // min(shrink, 16), 1, 1, 0])  # 128-token block x head
             dout = rnd(B, L, H, d)
             if args.impl == "ours":
                 fn = mod.stripe_flash_attn_qkvpacked_func

@@ -20,3 +20,8 @@ for impl in ours reference; do
 done
 echo "== sliding-window kernel variants inside the fused 2-GPU launch"
 RFA_B200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 600 -k "sliding_window_kernels" > gpurun_out/pytest_window_multi.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_window_multi.log
+echo "== stripe fp8 config, forward only: dequantise path vs fp8 forward kernel (per-head descales)"
+for lvl in 0 1 2; do
+  RFA_B200_FP8_KERNEL=$lvl timeout 600 $TR --master-port 29544 benchmark/bench_configs.py --only stripe8 --forward-only --fp8-per-head > gpurun_out/bench_stripe8_fp8kernel$lvl.jsonl 2> gpurun_out/bench_stripe8_fp8kernel$lvl.err
+  grep '^{' gpurun_out/bench_stripe8_fp8kernel$lvl.jsonl | cut -c1-220
+done
