@@ -211,31 +211,48 @@ def _window(window_size) -> Tuple[int, int]:
     return (-1 if left < 0 else left, -1 if right < 0 else right)
 
 
+# Plans are cached per (scheme, rank, shapes, ...).  Each plan also knows how to produce its peers' plans
+# (``plan.peer(r)``): the fused path derives from them which K/V rows every peer needs and which dK/dV rows every
+# peer will send back, without any exchange at run time.
+
 @functools.lru_cache(maxsize=512)
 def _batch_plan(scheme, rank, world, batch, seqlen, causal, window=(-1, -1)):
     if scheme == "ring":
-        return P.plan_ring(rank, world, batch, seqlen, causal, window)
-    if scheme == "zigzag":
-        return P.plan_zigzag(rank, world, batch, seqlen, window)
-    if scheme == "stripe":
-        return P.plan_stripe(rank, world, batch, seqlen, window)
-    raise ValueError(scheme)
+        plan = P.plan_ring(rank, world, batch, seqlen, causal, window)
+    elif scheme == "zigzag":
+        plan = P.plan_zigzag(rank, world, batch, seqlen, window)
+    elif scheme == "stripe":
+        plan = P.plan_stripe(rank, world, batch, seqlen, window)
+    else:
+        raise ValueError(scheme)
+    plan.peer = lambda r: _batch_plan(scheme, r, world, batch, seqlen, causal, window)
+    return plan
 
 
 @functools.lru_cache(maxsize=512)
 def _varlen_plan(scheme, rank, world, cu, causal, window=(-1, -1)):
     if scheme == "ring":
-        return P.plan_ring_varlen(rank, world, cu, causal, window)
-    if scheme == "zigzag":
-        return P.plan_zigzag_varlen(rank, world, cu, window)
-    raise ValueError(scheme)
+        plan = P.plan_ring_varlen(rank, world, cu, causal, window)
+    elif scheme == "zigzag":
+        plan = P.plan_zigzag_varlen(rank, world, cu, window)
+    else:
+        raise ValueError(scheme)
+    plan.peer = lambda r: _varlen_plan(scheme, r, world, cu, causal, window)
+    return plan
 
 
 @functools.lru_cache(maxsize=512)
 def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=None, window=(-1, -1)):
     # global_cu is part of the cache key on purpose: plans with equal local content but different global
     # layouts must not share their per-plan caches (peers' needs, push tables)
-    return P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal, window)
+    plan = P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal, window)
+    if global_cu is not None:
+        plan.peer = lambda r: _llama3_peer_plan(global_cu, causal, r, world, tokens, window)
+    elif world > 1:
+        # global layout unknown (cu tensors not produced by prepare()): the peers' needs cannot be derived
+        # locally, so such calls use the torch.distributed all-gather transport around the same kernels
+        plan.fused_ok = False
+    return plan
 
 
 def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
@@ -248,7 +265,6 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
     b, s, hq, d = q.shape
     win = _window(window_size)
     plan = _batch_plan(scheme, rank, world, b, s, bool(causal), win)
-    plan.peer = lambda r, _a=(scheme, world, b, s, bool(causal), win): _batch_plan(_a[0], r, *_a[1:])
     out, lse = _cp_apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
                                  v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
                                  "ring", 1, deterministic, fp8)
@@ -268,7 +284,6 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
     cu_host = cu_seqlens_to_host(cu_seqlens)
     win = _window(window_size)
     plan = _varlen_plan(scheme, rank, world, cu_host, bool(causal), win)
-    plan.peer = lambda r, _a=(scheme, world, cu_host, bool(causal), win): _varlen_plan(_a[0], r, *_a[1:])
     if plan.q_rows != q.shape[0]:
         raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
     out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic, fp8)
@@ -402,10 +417,11 @@ def llama3_flash_attn_prepare_cu_seqlens(cu_seqlens: torch.Tensor, causal: bool,
 
 
 @functools.lru_cache(maxsize=512)
-def _llama3_peer_plan(global_cu, causal, rank, world, tokens):
+def _llama3_peer_plan(global_cu, causal, rank, world, tokens, window=(-1, -1)):
     cq, ck, _mq, _mk, ks = llama3_flash_attn_prepare_cu_seqlens(torch.tensor(global_cu, dtype=torch.int32), causal,
                                                                rank, world)
-    return _llama3_plan(rank, world, tokens, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), causal, global_cu)
+    return _llama3_plan(rank, world, tokens, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), causal, global_cu,
+                        window)
 
 
 def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
@@ -426,12 +442,6 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
         glob = hit[0]
     plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal), glob,
                         _window(window_size))
-    if glob is not None:
-        plan.peer = lambda r, _g=glob, _w=world, _c=bool(causal), _t=q.shape[0]: _llama3_peer_plan(_g, _c, r, _w, _t)
-    elif world > 1:
-        # global layout unknown (cu tensors not produced by prepare()): the peers' needs cannot be derived
-        # locally, so this call uses the torch.distributed all-gather transport around the same kernels
-        plan.fused_ok = False
     out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
                                  int(heads_k_stride), deterministic, fp8)
     return (out, lse, None) if return_attn_probs else out

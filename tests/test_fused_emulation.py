@@ -44,24 +44,10 @@ def _fwd_rank(fake, q, k, v, k_stage, v_stage, items, segs, seg_lo, scale, hq):
     return out, lse
 
 
-@pytest.mark.parametrize("scheme", ["zigzag", "ring", "stripe"])
-@pytest.mark.parametrize("window", [(-1, -1), (150, 0), (700, 0)])
-def test_fused_tables_end_to_end(scheme, window):
-    world, L, hq, hkv = 4, 384, 4, 2
-    S = world * L
-    torch.manual_seed(0)
-    q, k, v, dout = (torch.randn(1, S, h, D) for h in (hq, hkv, hkv, hq))
-    rq, rk, rv = (t.clone().requires_grad_(True) for t in (q, k, v))
-    ref, ref_lse = attention_oracle(rq, rk, rv, True, window_size=window)
-    ref.backward(dout)
-    shard = getattr(layouts, f"shard_{scheme}")
-    plans = _plans(scheme, world, L, window)
+def _replay(plans, world, L, hq, hkv, lq, lk, lv, ldo, ref_out, ref_lse, ref_dq, ref_dk, ref_dv):
+    """Run forward + backward of every rank from its tables; ``l*`` / ``ref_*`` are per-rank lists."""
     fake = FakeExt()
     scale = D ** -0.5
-    lq = [shard(q, r, world)[0] for r in range(world)]
-    lk = [shard(k, r, world)[0] for r in range(world)]
-    lv = [shard(v, r, world)[0] for r in range(world)]
-    ldo = [shard(dout, r, world)[0] for r in range(world)]
     row_bytes = hkv * D * 4
     # ---- push: every rank copies the rows its peers need into their staging slot [src = me]
     stage_k = [torch.full((world * L, hkv, D), float("nan")) for _ in range(world)]
@@ -88,13 +74,12 @@ def test_fused_tables_end_to_end(scheme, window):
             seg_lo = None
         o, l = _fwd_rank(fake, lq[me], lk[me], lv[me], stage_k[me], stage_v[me], items, segs, seg_lo, scale, hq)
         assert not torch.isnan(o).any(), "a forward segment read staging rows nobody pushed"
-        torch.testing.assert_close(o, shard(ref, me, world)[0], atol=2e-5, rtol=2e-4)
-        torch.testing.assert_close(l, shard(ref_lse, me, world, dim=2)[0], atol=1e-4, rtol=1e-4)
+        torch.testing.assert_close(o, ref_out[me], atol=2e-5, rtol=2e-4)
+        torch.testing.assert_close(l, ref_lse[me], atol=1e-4, rtol=1e-4)
         outs.append(o)
         lses.append(l)
     # ---- backward: tiles write into the owner's inbox slot [src = me]; owners reduce
     inbox = [torch.full((world, 2, L, hkv, D), float("nan")) for _ in range(world)]  # [owner][slot][dK|dV]
-    dqs = []
     for me, p in enumerate(plans):
         offsets = {s: (0 if s == me else s * L) for s in range(world)}
         flags = {s: s for s in range(world) if s != me}
@@ -118,8 +103,7 @@ def test_fused_tables_end_to_end(scheme, window):
                 fake._bwd(lq[me], ldo[me], kk, vv, dq, one, qs, lses[me], delta, dk_t, dv_t, scale, win)
             inbox[owner][me, 0, out_row0:out_row0 + kv_rows] = dk_t[src_row:src_row + kv_rows]
             inbox[owner][me, 1, out_row0:out_row0 + kv_rows] = dv_t[src_row:src_row + kv_rows]
-        dqs.append(dq)
-        torch.testing.assert_close(dq, shard(rq.grad, me, world)[0], atol=5e-5, rtol=5e-4)
+        torch.testing.assert_close(dq, ref_dq[me], atol=5e-5, rtol=5e-4)
     for me, p in enumerate(plans):
         tasks = symm.reduce_tasks(p, _Ctx(), torch.device("cpu")).tolist()
         dk, dv = torch.zeros(L, hkv, D), torch.zeros(L, hkv, D)
@@ -130,8 +114,51 @@ def test_fused_tables_end_to_end(scheme, window):
                     assert not torch.isnan(part_k).any(), "the reduction reads inbox rows no peer wrote"
                     dk[row0:row0 + rows] += part_k
                     dv[row0:row0 + rows] += part_v
-        torch.testing.assert_close(dk, shard(rk.grad, me, world)[0], atol=5e-5, rtol=5e-4)
-        torch.testing.assert_close(dv, shard(rv.grad, me, world)[0], atol=5e-5, rtol=5e-4)
+        torch.testing.assert_close(dk, ref_dk[me], atol=5e-5, rtol=5e-4)
+        torch.testing.assert_close(dv, ref_dv[me], atol=5e-5, rtol=5e-4)
+
+
+@pytest.mark.parametrize("scheme", ["zigzag", "ring", "stripe"])
+@pytest.mark.parametrize("window", [(-1, -1), (150, 0), (700, 0)])
+def test_fused_tables_end_to_end(scheme, window):
+    world, L, hq, hkv = 4, 384, 4, 2
+    S = world * L
+    torch.manual_seed(0)
+    q, k, v, dout = (torch.randn(1, S, h, D) for h in (hq, hkv, hkv, hq))
+    rq, rk, rv = (t.clone().requires_grad_(True) for t in (q, k, v))
+    ref, ref_lse = attention_oracle(rq, rk, rv, True, window_size=window)
+    ref.backward(dout)
+    shard = getattr(layouts, f"shard_{scheme}")
+    R = range(world)
+    _replay(_plans(scheme, world, L, window), world, L, hq, hkv,
+            [shard(q, r, world)[0] for r in R], [shard(k, r, world)[0] for r in R], [shard(v, r, world)[0] for r in R],
+            [shard(dout, r, world)[0] for r in R], [shard(ref, r, world)[0] for r in R],
+            [shard(ref_lse, r, world, dim=2)[0] for r in R], [shard(rq.grad, r, world)[0] for r in R],
+            [shard(rk.grad, r, world)[0] for r in R], [shard(rv.grad, r, world)[0] for r in R])
+
+
+@pytest.mark.parametrize("window", [(-1, -1), (200, 0)])
+def test_fused_tables_llama3(window):
+    """llama3 layout (contiguous split of packed documents): peers' plans come from the global cu_seqlens that
+    prepare() attaches, exactly as parallel/api.py derives them at run time."""
+    from ring_flash_attn_b200.ops.dense import varlen_attention_oracle
+    from ring_flash_attn_b200.parallel import api
+
+    world, L, hq, hkv = 4, 256, 4, 2
+    S = world * L
+    cu = (0, 300, 301, 777, S)
+    torch.manual_seed(0)
+    q, k, v, dout = (torch.randn(S, h, D) for h in (hq, hkv, hkv, hq))
+    rq, rk, rv = (t.clone().requires_grad_(True) for t in (q, k, v))
+    ref, ref_lse = varlen_attention_oracle(rq, rk, rv, torch.tensor(cu), True, window_size=window)
+    ref.backward(dout)
+    plans = [api._llama3_peer_plan(cu, True, r, world, L, window) for r in range(world)]
+    sh = lambda x, r: layouts.shard_llama3(x, r, world)  # noqa: E731
+    R = range(world)
+    _replay(plans, world, L, hq, hkv, [sh(q, r) for r in R], [sh(k, r) for r in R], [sh(v, r) for r in R],
+            [sh(dout, r) for r in R], [sh(ref, r) for r in R],
+            [sh(ref_lse.transpose(0, 1), r).transpose(0, 1) for r in R], [sh(rq.grad, r) for r in R],
+            [sh(rk.grad, r) for r in R], [sh(rv.grad, r) for r in R])
 
 
 def test_visible_helper_matches_lo_none():
