@@ -276,3 +276,59 @@ def plan_llama3(rank: int, world: int, tokens_local: int, cu_seqlens_q: Sequence
             if s == src:
                 _add(plan, d, src, r0, n, vis)
     return plan
+
+
+# ----------------------------------------------------------------------------------------------
+# flat layouts: every rank owns a list of ranges of the packed token stream
+# ----------------------------------------------------------------------------------------------
+
+def zigzag_flat_ranges(rank: int, world: int, total: int) -> List[Tuple[int, int]]:
+    """Chunks ``rank`` and ``2W-1-rank`` of the flat stream cut into ``2W`` equal chunks."""
+    if total % (2 * world):
+        raise ValueError(f"total tokens ({total}) must be divisible by 2 * world_size ({2 * world})")
+    c = total // (2 * world)
+    return [(rank * c, (rank + 1) * c), ((2 * world - 1 - rank) * c, (2 * world - rank) * c)]
+
+
+def plan_flat(rank: int, world: int, global_cu: Sequence[int], ranges_of, causal: bool,
+              window: Tuple[int, int] = (-1, -1)) -> CPPlan:
+    """Packed documents (``global_cu``) over a flat token stream where rank r owns ``ranges_of(r)`` - a list of
+    ``[g0, g1)`` global ranges stored back to back in its local tensors.  Documents may be cut anywhere.
+
+    With ``zigzag_flat_ranges`` this is the load-balanced llama3 variant the reference lists as a TODO
+    (/root/reference/README.md:130): the causal work of every rank is equal for any packing, and no document length
+    has to be divisible by the world size."""
+    cu = [int(x) for x in global_cu]
+    owned = [ranges_of(r) for r in range(world)]
+    L = sum(b - a for a, b in owned[rank])
+    if any(sum(b - a for a, b in o) != L for o in owned):
+        raise ValueError("every rank must own the same number of tokens")
+    plan = CPPlan(world, rank, L, L)
+    # local query chunks: (owned range x document) pieces
+    q_pieces = []  # (chunk index, global start, rows)
+    base = 0
+    for a, b in owned[rank]:
+        for d0, d1 in zip(cu[:-1], cu[1:]):
+            lo, hi = max(a, d0), min(b, d1)
+            if hi > lo:
+                q_pieces.append((len(plan.q_chunks), lo, hi - lo, d0, d1))
+                plan.q_chunks.append(QChunk(base + lo - a, hi - lo))
+        base += b - a
+    for src in _src_order(rank, world):
+        kbase = 0
+        for ka, kb in owned[src]:
+            for ci, q0, qn, d0, d1 in q_pieces:
+                lo, hi = max(ka, d0), min(kb, d1)
+                if hi > lo:
+                    vis = _classify(q0 - d0, qn, lo - d0, hi - lo, causal, window=window) \
+                        if (causal or window != (-1, -1)) else (None, None)
+                    _add(plan, ci, src, kbase + lo - ka, hi - lo, vis)
+            kbase += kb - ka
+    return plan
+
+
+def plan_zigzag_llama3(rank: int, world: int, global_cu: Sequence[int], causal: bool = True,
+                       window: Tuple[int, int] = (-1, -1)) -> CPPlan:
+    total = int(global_cu[-1])
+    return plan_flat(rank, world, global_cu, lambda r: zigzag_flat_ranges(r, world, total), causal, window)
+

@@ -31,6 +31,9 @@ __all__ = [
     "zigzag_ring_flash_attn_varlen_qkvpacked_func",
     "llama3_flash_attn_varlen_func", "llama3_flash_attn_varlen_kvpacked_func",
     "llama3_flash_attn_varlen_qkvpacked_func", "llama3_flash_attn_prepare_cu_seqlens",
+    # beyond the reference (its README lists "zigzag llama3" as a TODO)
+    "zigzag_llama3_flash_attn_varlen_func", "zigzag_llama3_flash_attn_varlen_kvpacked_func",
+    "zigzag_llama3_flash_attn_varlen_qkvpacked_func",
 ]
 
 
@@ -238,6 +241,13 @@ def _varlen_plan(scheme, rank, world, cu, causal, window=(-1, -1)):
     else:
         raise ValueError(scheme)
     plan.peer = lambda r: _varlen_plan(scheme, r, world, cu, causal, window)
+    return plan
+
+
+@functools.lru_cache(maxsize=512)
+def _zigzag_llama3_plan(rank, world, global_cu, causal, window=(-1, -1)):
+    plan = P.plan_zigzag_llama3(rank, world, global_cu, causal, window)
+    plan.peer = lambda r: _zigzag_llama3_plan(r, world, global_cu, causal, window)
     return plan
 
 
@@ -473,3 +483,52 @@ def llama3_flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens_q, cu_seqlens_k, max
                                          max_seqlen_q, max_seqlen_k, heads_k_stride, local_k_slice, dropout_p,
                                          softmax_scale, causal, window_size, alibi_slopes, deterministic,
                                          return_attn_probs, group, descale=_split_descale(descale, 1, 3))
+
+
+# ----------------------------------------------------------------------------------------------
+# zigzag llama3: flat packed stream, rank r holds chunks r and 2W-1-r of 2W (beyond the reference)
+# ----------------------------------------------------------------------------------------------
+
+def zigzag_llama3_flash_attn_varlen_func(q, k, v, cu_seqlens, dropout_p=0.0, softmax_scale=None, causal=True,
+                                         window_size=(-1, -1), alibi_slopes=None, deterministic=False,
+                                         return_attn_probs=False, group=None, *, descale=None):
+    """Load-balanced context parallelism for packed documents of ARBITRARY lengths.
+
+    The flat token stream (all documents back to back, ``cu_seqlens`` = the GLOBAL cumulative lengths, the same on
+    every rank) is cut into ``2 * world_size`` equal chunks and rank r holds chunks ``r`` and ``2W-1-r``
+    (``parallel.layouts.shard_zigzag_llama3``).  Unlike the llama3 layout every rank does the same amount of causal
+    work, and unlike the zigzag varlen layout no document length has to be divisible by ``2 * world_size``.
+    q (T_local, Hq, D), k / v (T_local, Hkv, D); returns out (and (out, lse (Hq, T_local), None))."""
+    _check_common(q, dropout_p, window_size, alibi_slopes)
+    q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
+    rank, world = group_info(group)
+    cu_host = cu_seqlens_to_host(cu_seqlens)
+    if cu_host[-1] != q.shape[0] * world:
+        raise ValueError(f"cu_seqlens[-1]={cu_host[-1]} must equal local tokens ({q.shape[0]}) x world size ({world}): "
+                         "this entry point takes the GLOBAL cu_seqlens")
+    plan = _zigzag_llama3_plan(rank, world, cu_host, bool(causal), _window(window_size))
+    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic, fp8)
+    return (out, lse, None) if return_attn_probs else out
+
+
+def zigzag_llama3_flash_attn_varlen_kvpacked_func(q, kv, cu_seqlens, dropout_p=0.0, softmax_scale=None, causal=True,
+                                                  window_size=(-1, -1), alibi_slopes=None, deterministic=False,
+                                                  return_attn_probs=False, group=None, *, descale=None):
+    """kv (T_local, 2, Hkv, D) variant of :func:`zigzag_llama3_flash_attn_varlen_func`."""
+    if descale is not None:
+        dq, dkv = descale
+        dk, dv = _split_descale(dkv, 1, 2)
+        descale = (dq, dk, dv)
+    return zigzag_llama3_flash_attn_varlen_func(q, kv[:, 0], kv[:, 1], cu_seqlens, dropout_p, softmax_scale, causal,
+                                                window_size, alibi_slopes, deterministic, return_attn_probs, group,
+                                                descale=descale)
+
+
+def zigzag_llama3_flash_attn_varlen_qkvpacked_func(qkv, cu_seqlens, dropout_p=0.0, softmax_scale=None, causal=True,
+                                                   window_size=(-1, -1), alibi_slopes=None, deterministic=False,
+                                                   return_attn_probs=False, group=None, *, descale=None):
+    """qkv (T_local, 3, H, D) variant of :func:`zigzag_llama3_flash_attn_varlen_func`."""
+    return zigzag_llama3_flash_attn_varlen_func(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens, dropout_p, softmax_scale,
+                                                causal, window_size, alibi_slopes, deterministic, return_attn_probs,
+                                                group, descale=_split_descale(descale, 1, 3))
+

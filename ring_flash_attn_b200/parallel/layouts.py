@@ -45,6 +45,21 @@ def shard_llama3(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     return x.chunk(world, dim=0)[rank].contiguous()
 
 
+def shard_zigzag_llama3(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Flat packed stream (T, ...): chunks ``rank`` and ``2W-1-rank`` of ``2W`` (zigzag_llama3_* entry points)."""
+    return shard_zigzag(x, rank, world, dim=0)
+
+
+def positions_zigzag_llama3(cu_seqlens: Sequence[int], rank: int, world: int, device=None) -> torch.Tensor:
+    """Position inside its document of every local token of the zigzag-llama3 layout (what RoPE needs)."""
+    cu = torch.as_tensor([int(c) for c in cu_seqlens], dtype=torch.long)
+    total = int(cu[-1])
+    flat = torch.arange(total)
+    pos = flat - cu[torch.searchsorted(cu, flat, right=True) - 1]
+    out = shard_zigzag_llama3(pos, rank, world)
+    return out if device is None else out.to(device)
+
+
 def positions(scheme: str, rank: int, world: int, seqlen_local: int, device=None) -> torch.Tensor:
     """Global position of every local token (what RoPE needs), batch layouts."""
     i = torch.arange(seqlen_local, device=device)

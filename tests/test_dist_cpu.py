@@ -245,6 +245,63 @@ def test_sliding_window(world):
     run_distributed(_all_window_cases, world)
 
 
+def _zigzag_llama3_case(rank, world, causal, packing, hq, hkv, window=(-1, -1)):
+    torch.manual_seed(0)
+    d = 8
+    total = 2 * world * 11
+    cu = [0, 7, 8, total // 2 + 3, total]  # arbitrary document lengths, cut anywhere by the chunk boundaries
+    q = _bcast(torch.randn(total, hq, d))
+    k = _bcast(torch.randn(total, hkv, d))
+    v = _bcast(torch.randn(total, hkv, d))
+    dout = _bcast(torch.randn(total, hq, d))
+    cu_t = torch.tensor(cu, dtype=torch.int32)
+    qr, kr, vr = (x.detach().clone().requires_grad_(True) for x in (q, k, v))
+    ref_out, ref_lse = varlen_attention_oracle(qr, kr, vr, cu_t, causal, window_size=window)
+    ref_out.backward(dout)
+    sh = lambda x: layouts.shard_zigzag_llama3(x, rank, world)  # noqa: E731
+    lq, lk, lv = (sh(x).detach().requires_grad_(True) for x in (q, k, v))
+    if packing == "qkv":
+        qkv = torch.stack([lq, lk, lv], dim=1).detach().requires_grad_(True)
+        out, lse, _ = rfa.zigzag_llama3_flash_attn_varlen_qkvpacked_func(qkv, cu_t, causal=causal, window_size=window,
+                                                                         return_attn_probs=True)
+    elif packing == "kv":
+        kv = torch.stack([lk, lv], dim=1).detach().requires_grad_(True)
+        out, lse, _ = rfa.zigzag_llama3_flash_attn_varlen_kvpacked_func(lq, kv, cu_t, causal=causal,
+                                                                        window_size=window, return_attn_probs=True)
+    else:
+        out, lse, _ = rfa.zigzag_llama3_flash_attn_varlen_func(lq, lk, lv, cu_t, causal=causal, window_size=window,
+                                                               return_attn_probs=True)
+    out.backward(sh(dout))
+    if packing == "qkv":
+        gq, gk, gv = qkv.grad[:, 0], qkv.grad[:, 1], qkv.grad[:, 2]
+    elif packing == "kv":
+        gq, gk, gv = lq.grad, kv.grad[:, 0], kv.grad[:, 1]
+    else:
+        gq, gk, gv = lq.grad, lk.grad, lv.grad
+    torch.testing.assert_close(out, sh(ref_out), **TOL)
+    torch.testing.assert_close(lse, sh(ref_lse.transpose(0, 1)).transpose(0, 1), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gq, sh(qr.grad), **TOL)
+    torch.testing.assert_close(gk, sh(kr.grad), **TOL)
+    torch.testing.assert_close(gv, sh(vr.grad), **TOL)
+    # RoPE helper: position of every local token inside its document
+    pos = torch.cat([torch.arange(b - a) for a, b in zip(cu[:-1], cu[1:])])
+    assert torch.equal(layouts.positions_zigzag_llama3(cu, rank, world), sh(pos))
+
+
+def _all_zigzag_llama3_cases(rank, world):
+    _zigzag_llama3_case(rank, world, True, "qkv", 4, 4)
+    _zigzag_llama3_case(rank, world, True, "kv", 4, 2)
+    _zigzag_llama3_case(rank, world, False, "none", 2, 1)
+    _zigzag_llama3_case(rank, world, True, "none", 2, 2, (6, 0))
+    _zigzag_llama3_case(rank, world, False, "kv", 2, 2, (4, 3))
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_zigzag_llama3(world):
+    """Beyond the reference (its README TODO): zigzag over the flat packed stream, arbitrary document lengths."""
+    run_distributed(_all_zigzag_llama3_cases, world)
+
+
 def _single_process_case():
     # world_size 1 without any process group: every scheme degenerates to plain attention
     torch.manual_seed(0)

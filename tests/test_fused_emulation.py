@@ -161,5 +161,27 @@ def test_fused_tables_llama3(window):
             [sh(rk.grad, r) for r in R], [sh(rv.grad, r) for r in R])
 
 
+@pytest.mark.parametrize("window", [(-1, -1), (200, 0)])
+def test_fused_tables_zigzag_llama3(window):
+    from ring_flash_attn_b200.ops.dense import varlen_attention_oracle
+    from ring_flash_attn_b200.parallel import api
+
+    world, L, hq, hkv = 4, 256, 4, 2
+    S = world * L
+    cu = (0, 130, 131, 700, S)
+    torch.manual_seed(0)
+    q, k, v, dout = (torch.randn(S, h, D) for h in (hq, hkv, hkv, hq))
+    rq, rk, rv = (t.clone().requires_grad_(True) for t in (q, k, v))
+    ref, ref_lse = varlen_attention_oracle(rq, rk, rv, torch.tensor(cu), True, window_size=window)
+    ref.backward(dout)
+    plans = [api._zigzag_llama3_plan(r, world, cu, True, window) for r in range(world)]
+    sh = lambda x, r: layouts.shard_zigzag_llama3(x, r, world)  # noqa: E731
+    R = range(world)
+    _replay(plans, world, L, hq, hkv, [sh(q, r) for r in R], [sh(k, r) for r in R], [sh(v, r) for r in R],
+            [sh(dout, r) for r in R], [sh(ref, r) for r in R],
+            [sh(ref_lse.transpose(0, 1), r).transpose(0, 1) for r in R], [sh(rq.grad, r) for r in R],
+            [sh(rk.grad, r) for r in R], [sh(rv.grad, r) for r in R])
+
+
 def test_visible_helper_matches_lo_none():
     assert bool(_visible(4, 0, 6, 1 << 29, LO_NONE).all())

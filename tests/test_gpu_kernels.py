@@ -202,6 +202,26 @@ def test_world1_small_head_dim_runs_on_kernels(d):
     assert (qkv.grad.float() - ref.grad).abs().max().item() < 5e-2 * ref.grad.abs().max().item() + 2e-2
 
 
+def test_world1_zigzag_llama3():
+    """Flat zigzag layout over packed documents of arbitrary lengths (beyond the reference): same kernels, the
+    layout only changes the work tables."""
+    torch.manual_seed(0)
+    T, H, HK = 2048, 8, 2
+    cu = torch.tensor([0, 333, 334, 1500, T], dtype=torch.int32, device="cuda")
+    q = torch.randn(T, H, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    kv = torch.randn(T, 2, HK, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(T, H, 128, device="cuda").to(torch.bfloat16)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    ref, ref_lse = varlen_attention_oracle(rq, rkv[:, 0], rkv[:, 1], cu.cpu(), True)
+    ref.backward(dout.float())
+    out, lse, _ = rfa.zigzag_llama3_flash_attn_varlen_kvpacked_func(q, kv, cu, causal=True, return_attn_probs=True)
+    out.backward(dout)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
+    assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
+
+
 _EXPERIMENTAL = pytest.mark.skipif(
     __import__("os").environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
     reason="kernel variants written after the last hardware session; enable with RFA_B200_TEST_EXPERIMENTAL=1")

@@ -155,6 +155,43 @@ def test_varlen_schemes_2gpu(p2p):
     run_distributed(_all_varlen_cases, 2, p2p, backend="nccl")
 
 
+def _zigzag_llama3_case(rank, world, p2p):
+    os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    T, H, HK = 1024 * world, 8, 2
+    cu = torch.tensor([0, 777, 778, T // 2 + 5, T], dtype=torch.int32)
+    q = torch.randn(T, H, 128, device=dev)
+    k = torch.randn(T, HK, 128, device=dev)
+    v = torch.randn(T, HK, 128, device=dev)
+    dout = torch.randn(T, H, 128, device=dev)
+    for t in (q, k, v, dout):
+        dist.broadcast(t, src=0)
+    q, k, v, dout = (t.to(torch.bfloat16) for t in (q, k, v, dout))
+    rq, rk, rv = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref, ref_lse = varlen_attention_oracle(rq, rk, rv, cu, True)
+    ref.backward(dout.float())
+    sh = lambda x: layouts.shard_zigzag_llama3(x, rank, world)  # noqa: E731
+    for _ in range(2):
+        lq, lk, lv = (sh(t).detach().requires_grad_(True) for t in (q, k, v))
+        out, lse, _ = rfa.zigzag_llama3_flash_attn_varlen_func(lq, lk, lv, cu.to(dev), causal=True,
+                                                               return_attn_probs=True)
+        out.backward(sh(dout))
+        torch.cuda.synchronize()
+        _close(out, sh(ref), "out")
+        _close(lse, sh(ref_lse.transpose(0, 1)).transpose(0, 1), "lse", rel=2e-3, abs_=2e-3)
+        _close(lq.grad, sh(rq.grad), "dq")
+        _close(lk.grad, sh(rk.grad), "dk")
+        _close(lv.grad, sh(rv.grad), "dv")
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+def test_zigzag_llama3_2gpu(p2p):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_zigzag_llama3_case, 2, p2p, backend="nccl")
+
+
 def _window_fused_case(rank, world, p2p):
     os.environ["RFA_B200_WINDOW_KERNEL"] = "1"
     os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"

@@ -65,6 +65,18 @@ def _case(rank, world, window, expect):
     torch.testing.assert_close(out.float(), sh(ref), **BF16)
     for g, r in zip(l2, r2):
         _grad_close(g.grad, sh(r.grad))
+    # flat zigzag layout, documents of arbitrary lengths
+    gcu = torch.tensor([0, 77, 78, S // 2 + 9, S], dtype=torch.int32)
+    r3 = [t.float().requires_grad_(True) for t in (q2, k2, v2)]
+    ref, _ = varlen_attention_oracle(*r3, gcu, True, window_size=window)
+    ref.backward(dout[0].float())
+    sh3 = lambda x: layouts.shard_zigzag_llama3(x, rank, world)  # noqa: E731
+    l3 = [sh3(t).detach().requires_grad_(True) for t in (q2, k2, v2)]
+    out = rfa.zigzag_llama3_flash_attn_varlen_func(*l3, gcu, causal=True, window_size=window)
+    out.backward(sh3(dout[0]))
+    torch.testing.assert_close(out.float(), sh3(ref), **BF16)
+    for g, r in zip(l3, r3):
+        _grad_close(g.grad, sh3(r.grad))
 
 
 @pytest.mark.parametrize("world", [1, 2])

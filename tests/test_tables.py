@@ -193,6 +193,9 @@ def _replay_backward(items, qsegs, q_rows, kv_cols):
 
 def _window_plans(scheme, world, window):
     L = 600
+    if scheme == "zigzag_llama3":
+        cu = [0, 100, 101, (L * world * 13) // 24, L * world]
+        return [P.plan_zigzag_llama3(r, world, cu, True, window) for r in range(world)]
     if scheme == "ring":
         return [P.plan_ring(r, world, 1, L, window[1] == 0, window) for r in range(world)]
     if scheme == "zigzag":
@@ -205,7 +208,7 @@ def _window_plans(scheme, world, window):
     return [P.plan_zigzag_varlen(r, world, cu, window) for r in range(world)]
 
 
-@pytest.mark.parametrize("scheme", ["ring", "zigzag", "stripe", "ring_varlen", "zigzag_varlen"])
+@pytest.mark.parametrize("scheme", ["ring", "zigzag", "stripe", "ring_varlen", "zigzag_varlen", "zigzag_llama3"])
 @pytest.mark.parametrize("world", [1, 4])
 @pytest.mark.parametrize("window", [(37, 0), (300, 0), (1000, 0)])
 def test_window_tables_replay_matches_plan(scheme, world, window):
