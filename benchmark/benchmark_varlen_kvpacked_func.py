@@ -52,6 +52,8 @@ def main():
                 cq, ck, mq, mk, ks = llama3_args[j]
                 return rfa.llama3_flash_attn_varlen_kvpacked_func(q, kv, cq, ck, mq, mk, heads_k_stride=args.heads_k_stride,
                                                                  local_k_slice=ks, causal=True)
+            if name == "zigzag_llama3":  # beyond the reference: flat zigzag, global cu_seqlens
+                return rfa.zigzag_llama3_flash_attn_varlen_kvpacked_func(q, kv, global_cus[j], causal=True)
             cu = local_cus[j]
             mx = int((cu[1:] - cu[:-1]).max())
             fn = rfa.ring_flash_attn_varlen_kvpacked_func if name == "ring" else rfa.zigzag_ring_flash_attn_varlen_kvpacked_func
@@ -59,7 +61,7 @@ def main():
         return run
 
     res = {}
-    for name in ("ring", "zigzag_ring", "llama3"):
+    for name in ("ring", "zigzag_ring", "llama3", "zigzag_llama3"):
         run = make(name)
 
         def step(i):
