@@ -25,10 +25,15 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from ..parallel.api import llama3_flash_attn_prepare_cu_seqlens, llama3_flash_attn_varlen_func
+from ..parallel.api import (llama3_flash_attn_prepare_cu_seqlens, llama3_flash_attn_varlen_func,
+                            zigzag_llama3_flash_attn_varlen_func)
 
 DATA_PARAMS = {}
 RING_ATTN_SWITCH = True
+# "llama3" (the reference's layout: every rank feeds a contiguous slice of the packed stream) or "zigzag"
+# (extension: rank r feeds chunks r and 2W-1-r, see parallel.layouts.shard_zigzag_llama3 /
+# positions_zigzag_llama3 - balanced causal work); chosen in substitute_hf_flash_attn(..., layout=...)
+LAYOUT = "llama3"
 _ORIGINALS = {}
 
 
@@ -38,7 +43,7 @@ def update_ring_flash_attn_params(cu_seqlens: torch.Tensor, process_group: Optio
     rank = dist.get_rank(group=process_group) if dist.is_initialized() else 0
     cu_q, cu_k, max_q, max_k, k_slice = llama3_flash_attn_prepare_cu_seqlens(cu_seqlens, True, rank, world)
     DATA_PARAMS.update(cu_seqlens_q=cu_q, cu_seqlens_k=cu_k, max_seqlen_q=max_q, max_seqlen_k=max_k,
-                       local_k_slice=k_slice)
+                       local_k_slice=k_slice, cu_seqlens_global=cu_seqlens)
 
 
 def use_ring_attn(flag: bool) -> None:
@@ -65,6 +70,12 @@ def _ring_core(query_states, key_states, value_states, *, is_causal, dropout, so
         window = (int(sliding_window) - 1, 0)
     if deterministic is None:
         deterministic = os.environ.get("FLASH_ATTENTION_DETERMINISTIC", "0") == "1"
+    if LAYOUT == "zigzag":
+        out = zigzag_llama3_flash_attn_varlen_func(
+            query_states.squeeze(0), key_states.squeeze(0), value_states.squeeze(0),
+            DATA_PARAMS["cu_seqlens_global"], dropout_p=dropout, softmax_scale=softmax_scale, causal=True,
+            window_size=window, deterministic=deterministic, group=process_group)
+        return out.unsqueeze(0)
     out = llama3_flash_attn_varlen_func(
         query_states.squeeze(0), key_states.squeeze(0), value_states.squeeze(0),
         cu_seqlens_q=DATA_PARAMS["cu_seqlens_q"], cu_seqlens_k=DATA_PARAMS["cu_seqlens_k"],
@@ -143,8 +154,15 @@ def _make_interface_forward(process_group, heads_k_stride, stock):
     return flash_attention_forward
 
 
-def substitute_hf_flash_attn(process_group: Optional[dist.ProcessGroup], heads_k_stride: int):
-    """Patch ``transformers`` so that flash-attention layers run llama3-style context parallelism."""
+def substitute_hf_flash_attn(process_group: Optional[dist.ProcessGroup], heads_k_stride: int, layout: str = "llama3"):
+    """Patch ``transformers`` so that flash-attention layers run llama3-style context parallelism.
+
+    ``layout="zigzag"`` (extension) selects the balanced flat zigzag layout: feed every rank
+    ``layouts.shard_zigzag_llama3(input_ids)`` and ``layouts.positions_zigzag_llama3(cu_seqlens, rank, world)``."""
+    global LAYOUT
+    if layout not in ("llama3", "zigzag"):
+        raise ValueError("layout must be 'llama3' or 'zigzag'")
+    LAYOUT = layout
     try:
         import transformers
         import transformers.modeling_flash_attention_utils as fau
@@ -180,6 +198,9 @@ def substitute_hf_flash_attn(process_group: Optional[dist.ProcessGroup], heads_k
 def restore_hf_flash_attn() -> None:
     """Undo :func:`substitute_hf_flash_attn` (not in the reference; handy for tests)."""
     import transformers.modeling_flash_attention_utils as fau
+
+    global LAYOUT
+    LAYOUT = "llama3"
 
     old = _ORIGINALS.get("_flash_attention_forward")
     if old is not None:

@@ -95,3 +95,39 @@ def test_replacement_binds_any_signature_generation():
 @pytest.mark.parametrize("world", [1, 2])
 def test_tiny_llama_context_parallel(world):
     run_distributed(_case, world)
+
+
+def _zigzag_case(rank, world):
+    """layout="zigzag": every rank feeds chunks r and 2W-1-r of the packed stream with matching position ids."""
+    import ring_flash_attn_b200 as rfa
+    from ring_flash_attn_b200.models import hf_adapter
+    from ring_flash_attn_b200.parallel import layouts
+
+    model = _tiny_llama()
+    total = 48
+    cu = torch.tensor([0, 19, 48], dtype=torch.int32)
+    torch.manual_seed(1)
+    ids = torch.randint(0, 97, (1, total))
+    pos = torch.cat([torch.arange(19), torch.arange(29)]).unsqueeze(0)
+    mask = torch.full((total, total), float("-inf"))
+    for a, b in ((0, 19), (19, 48)):
+        mask[a:b, a:b] = torch.triu(torch.full((b - a, b - a), float("-inf")), diagonal=1)
+    with torch.no_grad():
+        ref = model(input_ids=ids, position_ids=pos, attention_mask=mask[None, None]).logits
+    rfa.substitute_hf_flash_attn(process_group=None, heads_k_stride=1, layout="zigzag")
+    model.config._attn_implementation = "flash_attention_2"
+    for layer in model.model.layers:
+        layer.self_attn.config._attn_implementation = "flash_attention_2"
+    rfa.update_ring_flash_attn_params(cu, None)
+    sh = lambda x: layouts.shard_zigzag_llama3(x, rank, world)  # noqa: E731
+    local_pos = layouts.positions_zigzag_llama3(cu.tolist(), rank, world).unsqueeze(0)
+    assert torch.equal(local_pos[0], sh(pos[0]))
+    with torch.no_grad():
+        out = model(input_ids=sh(ids[0]).unsqueeze(0), position_ids=local_pos).logits
+    torch.testing.assert_close(out[0], sh(ref[0]), atol=2e-4, rtol=2e-4)
+    hf_adapter.restore_hf_flash_attn()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_tiny_llama_zigzag_layout(world):
+    run_distributed(_zigzag_case, world)
