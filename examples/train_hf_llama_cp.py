@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--cuda", action="store_true")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tokens", type=int, default=0, help="packed tokens per step (default: 64 per rank on CPU)")
+    ap.add_argument("--layout", default="llama3", choices=["llama3", "zigzag"],
+                    help="llama3: contiguous slice per rank (the reference's layout); zigzag: chunks r and 2W-1-r of the "
+                         "packed stream (balanced causal work, extension)")
     args = ap.parse_args()
     from transformers import LlamaConfig, LlamaForCausalLM
 
@@ -51,14 +54,19 @@ def main():
     torch.manual_seed(0)  # same weights on every rank
     model = LlamaForCausalLM(cfg).to(dev, dtype)
     # route every attention layer through the context-parallel kernels
-    rfa.substitute_hf_flash_attn(process_group=None, heads_k_stride=1)
+    rfa.substitute_hf_flash_attn(process_group=None, heads_k_stride=1, layout=args.layout)
+    from ring_flash_attn_b200.parallel import layouts
+
+    def shard(x):  # (1, total) -> this rank's (1, L) tokens
+        if args.layout == "zigzag":
+            return layouts.shard_zigzag_llama3(x[0], rank, world).unsqueeze(0)
+        return x[:, rank * (x.shape[1] // world):(rank + 1) * (x.shape[1] // world)]
     model.config._attn_implementation = "flash_attention_2"
     for layer in model.model.layers:
         layer.self_attn.config._attn_implementation = "flash_attention_2"
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
 
     total = args.tokens or (64 if not args.cuda else 8192) * world
-    L = total // world
     gen = torch.Generator().manual_seed(1)
     for step in range(args.steps):
         # a packed batch: three documents of uneven length, identical on every rank
@@ -71,10 +79,9 @@ def main():
         labels[0, (cu[1:] - 1).long()] = -100  # the last token of a document has no target
 
         rfa.update_ring_flash_attn_params(cu.to(dev), None)  # once per batch, GLOBAL cu_seqlens
-        sl = slice(rank * L, (rank + 1) * L)
-        logits = model(input_ids=ids[:, sl].to(dev), position_ids=pos[:, sl].to(dev)).logits
+        logits = model(input_ids=shard(ids).to(dev), position_ids=shard(pos).to(dev)).logits
         loss_sum = torch.nn.functional.cross_entropy(logits.float().view(-1, cfg.vocab_size),
-                                                     labels[:, sl].to(dev).view(-1), ignore_index=-100,
+                                                     shard(labels).to(dev).reshape(-1), ignore_index=-100,
                                                      reduction="sum")
         n_targets = int((labels != -100).sum())
         (loss_sum / n_targets).backward()
