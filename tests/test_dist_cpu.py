@@ -302,6 +302,20 @@ def test_zigzag_llama3(world):
     run_distributed(_all_zigzag_llama3_cases, world)
 
 
+def _world3_cases(rank, world):
+    # a world size that is not a power of two: one case per scheme family
+    _batch_case(rank, world, "ring", True, "kv", 4, 2, torch.float32)
+    _batch_case(rank, world, "zigzag", True, "qkv", 2, 2, torch.float32)
+    _batch_case(rank, world, "stripe", True, "none", 4, 1, torch.float32, (7, 0))
+    _varlen_case(rank, world, "zigzag", True, "kv", 4, 2)
+    _llama3_case(rank, world, True, "none", 4, 2, 2)
+    _zigzag_llama3_case(rank, world, True, "kv", 4, 2)
+
+
+def test_world_size_three():
+    run_distributed(_world3_cases, 3)
+
+
 def _single_process_case():
     # world_size 1 without any process group: every scheme degenerates to plain attention
     torch.manual_seed(0)
