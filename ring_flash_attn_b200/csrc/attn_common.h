@@ -128,6 +128,8 @@ struct FwdParams {
   const int* seg_lo;  // sliding window only (else nullptr): per segment, key j visible to chunk row i iff j >= i + lo
   const float* head_scale_qk;  // fp8 only: q_descale * k_descale per QUERY head (multiplies the softmax scale)
   const float* head_scale_v;   // fp8 only: v_descale per KV head (multiplies the output)
+  int flags;  // experiment switches of the h64 forward (RFA_B200_FWD_FLAGS): bit 0 = no turn-taking between the
+              // two softmax warpgroups
   void* out;  // (rows, hq, 128) contiguous, input dtype
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;

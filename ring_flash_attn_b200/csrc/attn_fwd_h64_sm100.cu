@@ -306,17 +306,19 @@ attn_fwd_h64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     int n_pv = 0;  // halves handed to the MMA warp so far == P V GEMMs of this q-tile issued or about to be
 
     // The exp sections of the two warpgroups take turns (see attn_fwd_sm100.cu), one hand-off per 64-key step.
+    // With the next scores always ready the alternation may no longer pay: FwdParams::flags bit 0 disables it.
+    const bool turns = has_t1 && !(p.flags & 1);
     int handoffs_left = 0;
-    if (has_t1) {
+    if (turns) {
       for (int si = 0; si < it.seg_count; ++si)
         handoffs_left += 2 * seg_geom(p.segs[it.seg_begin + si], it).n_tiles;
       if (t == 1 && handoffs_left > 0) named_bar_arrive(1, 256);
     }
     auto turn_wait = [&]() {
-      if (has_t1) named_bar_sync(1 + t, 256);
+      if (turns) named_bar_sync(1 + t, 256);
     };
     auto turn_pass = [&]() {
-      if (has_t1) {
+      if (turns) {
         --handoffs_left;
         if (!(t == 1 && handoffs_left == 0)) named_bar_arrive(1 + (1 - t), 256);
       }

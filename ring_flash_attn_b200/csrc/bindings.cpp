@@ -128,6 +128,13 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
     return e != nullptr && std::atoi(e) != 0;
   }();
   auto* launch_fwd = (h64 && !fp8 && seg_lo == nullptr) ? &rfa::attn_fwd_h64_launch : &rfa::attn_fwd_launch;
+  {
+    static const int fwd_flags = [] {
+      const char* e = std::getenv("RFA_B200_FWD_FLAGS");
+      return e ? std::atoi(e) : 0;
+    }();
+    p.flags = fwd_flags;
+  }
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);

@@ -12,6 +12,7 @@ RFA_B200_FWD_H64=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu
 for h in 0 1; do
   RFA_B200_FWD_H64=$h RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_$h.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_$h.log 2>&1; echo "h64=$h exit $?"; grep -i "fwd" gpurun_out/first_look_h64_$h.log | head -8
 done
+RFA_B200_FWD_H64=1 RFA_B200_FWD_FLAGS=1 RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_noturn.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_noturn.log 2>&1; echo "h64 without turn-taking exit $?"; grep -i "fwd" gpurun_out/first_look_h64_noturn.log | head -4
 for poly in 1 2; do
   RFA_B200_FWD_H64=1 RFA_B200_POLY_EXP=$poly RFA_FIRST_LOOK_SKIP_FA2=1 RFA_FIRST_LOOK_OUT=gpurun_out/first_look_h64_poly$poly.json timeout 600 python benchmark/first_look.py > gpurun_out/first_look_h64_poly$poly.log 2>&1; echo "h64 poly=$poly exit $?"; grep -i "fwd" gpurun_out/first_look_h64_poly$poly.log | head -4
 done
