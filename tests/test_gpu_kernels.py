@@ -207,7 +207,7 @@ def test_world1_zigzag_llama3():
     layout only changes the work tables."""
     torch.manual_seed(0)
     T, H, HK = 2048, 8, 2
-    cu = torch.tensor([0, 333, 334, 1500, T], dtype=torch.int32, device="cuda")
+    cu = torch.tensor([0, 333, 420, 1500, T], dtype=torch.int32, device="cuda")
     q = torch.randn(T, H, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
     kv = torch.randn(T, 2, HK, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
     dout = torch.randn(T, H, 128, device="cuda").to(torch.bfloat16)

@@ -160,7 +160,7 @@ def _zigzag_llama3_case(rank, world, p2p):
     dev = torch.device("cuda", rank)
     torch.manual_seed(0)
     T, H, HK = 1024 * world, 8, 2
-    cu = torch.tensor([0, 777, 778, T // 2 + 5, T], dtype=torch.int32)
+    cu = torch.tensor([0, 777, 900, T // 2 + 5, T], dtype=torch.int32)
     q = torch.randn(T, H, 128, device=dev)
     k = torch.randn(T, HK, 128, device=dev)
     v = torch.randn(T, HK, 128, device=dev)
