@@ -3,7 +3,7 @@
 # (run under plain `gpurun`, 1 GPU): sliding window, fp8 (descriptor probe first), 64-key-step forward, direct dQ.
 mkdir -p gpurun_out
 echo "== experimental kernel variants written after the last round-1 hardware session (sliding window)"
-RFA_B200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "sliding_window_kernels" > gpurun_out/pytest_window.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_window.log
+RFA_B200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k "sliding_window_kernels or single_token" > gpurun_out/pytest_window.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_window.log
 echo "== fp8: kind::f8f6f4 descriptor probe (sweeps alternatives on a mismatch), then the fp8 forward kernel"
 timeout 300 python benchmark/probe_fp8.py > gpurun_out/probe_fp8.log 2>&1; echo "exit $?"; tail -4 gpurun_out/probe_fp8.log
 RFA_B200_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 500 -k "fp8" > gpurun_out/pytest_fp8.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_fp8.log

@@ -298,3 +298,23 @@ def test_fp8_forward_kernel(monkeypatch, per_head):
     torch.testing.assert_close(lse, ref_lse, atol=2e-2, rtol=2e-2)
     err = (out.float() - ref).abs().max().item()
     assert err < 6e-2 * ref.abs().max().item() + 2e-2, err
+
+
+@_EXPERIMENTAL
+def test_single_token_documents():
+    """Degenerate packing (documents of one token, chunks of one row): covered by the CPU table tests, run on hardware
+    with the other round-2 checks."""
+    torch.manual_seed(0)
+    T, H, HK = 1024, 4, 2
+    cu = torch.tensor([0, 1, 2, 333, 334, 700, T], dtype=torch.int32, device="cuda")
+    q = torch.randn(T, H, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    kv = torch.randn(T, 2, HK, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(T, H, 128, device="cuda").to(torch.bfloat16)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    ref, _ = varlen_attention_oracle(rq, rkv[:, 0], rkv[:, 1], cu.cpu(), True)
+    ref.backward(dout.float())
+    out = rfa.zigzag_llama3_flash_attn_varlen_kvpacked_func(q, kv, cu, causal=True)
+    out.backward(dout)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
+    assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
