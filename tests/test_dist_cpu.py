@@ -371,6 +371,33 @@ def test_head_dim_padding_reaches_engine(monkeypatch):
     assert seen[-1] == 24
 
 
+def test_custom_softmax_scale_and_lse_shapes():
+    """softmax_scale is forwarded (not the 1/sqrt(d) default); lse shapes follow flash-attn: (B, H, S) batch,
+    (H, T) varlen."""
+    torch.manual_seed(0)
+    q = torch.randn(2, 24, 4, 16, requires_grad=True)
+    kv = torch.randn(2, 24, 2, 2, 16)
+    ref, ref_lse = attention_oracle(q, kv[:, :, 0], kv[:, :, 1], True, softmax_scale=0.37)
+    out, lse, none = rfa.zigzag_ring_flash_attn_kvpacked_func(q, kv, softmax_scale=0.37, causal=True,
+                                                             return_attn_probs=True)
+    assert none is None and lse.shape == (2, 4, 24)
+    torch.testing.assert_close(out, ref, **TOL)
+    torch.testing.assert_close(lse, ref_lse, atol=1e-4, rtol=1e-4)
+    default = rfa.zigzag_ring_flash_attn_kvpacked_func(q, kv, causal=True)
+    assert not torch.allclose(default, out)
+    cu = torch.tensor([0, 10, 24], dtype=torch.int32)
+    qv, kvv = q[0].detach(), kv[0]
+    refv, refv_lse = varlen_attention_oracle(qv, kvv[:, 0], kvv[:, 1], cu, False, softmax_scale=1.3)
+    outv, lsev, _ = rfa.ring_flash_attn_varlen_kvpacked_func(qv, kvv, cu, 14, softmax_scale=1.3, causal=False,
+                                                            return_attn_probs=True)
+    assert lsev.shape == (4, 24)
+    torch.testing.assert_close(outv, refv, **TOL)
+    torch.testing.assert_close(lsev, refv_lse, atol=1e-4, rtol=1e-4)
+    # deterministic=True is accepted everywhere and does not change the result on this path
+    torch.testing.assert_close(rfa.ring_flash_attn_varlen_kvpacked_func(qv, kvv, cu, 14, softmax_scale=1.3,
+                                                                      deterministic=True), outv, **TOL)
+
+
 def test_single_process_no_group():
     _single_process_case()
 
