@@ -371,6 +371,34 @@ def test_head_dim_padding_reaches_engine(monkeypatch):
     assert seen[-1] == 24
 
 
+def _subgroup_case(rank, world):
+    """Two independent context-parallel groups inside one job (ranks {0,1} and {2,3}), as when CP is combined with
+    data parallelism: group ranks are translated to global ranks for the point-to-point transport
+    (/root/reference/ring_flash_attn/utils.py:109-111)."""
+    groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]  # collective: every rank creates both
+    g = groups[rank // 2]
+    grank, gworld = dist.get_rank(g), dist.get_world_size(g)
+    assert (grank, gworld) == (rank % 2, 2)
+    torch.manual_seed(100 + rank // 2)  # different data per group
+    qkv = torch.randn(1, 32, 3, 2, 16)
+    dist.broadcast(qkv, src=(rank // 2) * 2, group=g)
+    ref, _ = attention_oracle(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], True)
+    for scheme, fn in (("zigzag", rfa.zigzag_ring_flash_attn_qkvpacked_func), ("ring", rfa.ring_flash_attn_qkvpacked_func)):
+        shard = getattr(layouts, f"shard_{scheme}")
+        out = fn(shard(qkv, grank, gworld), causal=True, group=g)
+        torch.testing.assert_close(out, shard(ref, grank, gworld), **TOL)
+    cu = torch.tensor([0, 13, 32], dtype=torch.int32)
+    refv, _ = varlen_attention_oracle(qkv[0, :, 0], qkv[0, :, 1], qkv[0, :, 2], cu, True)
+    cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu, True, grank, gworld)
+    out = rfa.llama3_flash_attn_varlen_qkvpacked_func(layouts.shard_llama3(qkv[0], grank, gworld), cq, ck, mq, mk,
+                                                      heads_k_stride=1, local_k_slice=ks, causal=True, group=g)
+    torch.testing.assert_close(out, layouts.shard_llama3(refv, grank, gworld), **TOL)
+
+
+def test_process_subgroups():
+    run_distributed(_subgroup_case, 4)
+
+
 def test_custom_softmax_scale_and_lse_shapes():
     """softmax_scale is forwarded (not the 1/sqrt(d) default); lse shapes follow flash-attn: (B, H, S) batch,
     (H, T) varlen."""
