@@ -228,3 +228,32 @@ def test_sliding_window_kernels_2gpu(p2p):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     run_distributed(_window_fused_case, 2, p2p, backend="nccl")
+
+
+def _subgroup_fused_case(rank, world):
+    """Two fused context-parallel groups ({0,1} and {2,3}) side by side: separate peer contexts, staging buffers and
+    signal pads per group."""
+    os.environ["RFA_B200_DISABLE_P2P"] = "0"
+    groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    g = groups[rank // 2]
+    grank, gworld = dist.get_rank(g), 2
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(100 + rank // 2)
+    qkv = torch.randn(1, 2048, 3, 4, 128, device=dev)
+    dist.broadcast(qkv, src=(rank // 2) * 2, group=g)
+    qkv = qkv.to(torch.bfloat16)
+    ref, _ = attention_oracle(qkv[:, :, 0].float(), qkv[:, :, 1].float(), qkv[:, :, 2].float(), True)
+    for _ in range(3):
+        local = layouts.shard_zigzag(qkv, grank, gworld).detach().requires_grad_(True)
+        out = rfa.zigzag_ring_flash_attn_qkvpacked_func(local, causal=True, group=g)
+        out.sum().backward()
+        torch.cuda.synchronize()
+        _close(out, layouts.shard_zigzag(ref, grank, gworld), "out")
+
+
+@pytest.mark.skipif(os.environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="not yet run on hardware (RFA_B200_TEST_EXPERIMENTAL=1)")
+def test_fused_subgroups_4gpu():
+    if _ngpu() < 4:
+        pytest.skip("needs 4 GPUs")
+    run_distributed(_subgroup_fused_case, 4, backend="nccl")
