@@ -25,3 +25,7 @@ for lvl in 0 1 2; do
   RFA_B200_FP8_KERNEL=$lvl timeout 600 $TR --master-port 29544 benchmark/bench_configs.py --only stripe8 --forward-only --fp8-per-head > gpurun_out/bench_stripe8_fp8kernel$lvl.jsonl 2> gpurun_out/bench_stripe8_fp8kernel$lvl.err
   grep '^{' gpurun_out/bench_stripe8_fp8kernel$lvl.jsonl | cut -c1-220
 done
+if [ "$N" -ge 4 ]; then
+  echo "== two fused context-parallel subgroups side by side (first hardware run)"
+  RFA_B200_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 500 -k "fused_subgroups" > gpurun_out/pytest_subgroups.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest_subgroups.log
+fi
