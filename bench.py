@@ -291,7 +291,13 @@ def main():
             except Exception as exc:  # noqa: BLE001 - never lose the benchmark line over the input pipeline
                 run_e2e = e2e_step
                 pipeline = f"serial copy -> compute (prefetch unavailable: {type(exc).__name__})"
-        e2e_ms = timed(run_e2e, args.steps, warm)
+        try:
+            e2e_ms = timed(run_e2e, args.steps, warm)
+        except Exception as exc:  # noqa: BLE001 - fall back to the serial loop rather than lose the line
+            if run_e2e is e2e_step:
+                raise
+            pipeline = f"serial copy -> compute (prefetch failed while timing: {type(exc).__name__})"
+            e2e_ms = timed(e2e_step, args.steps, warm)
         e2e = {"value": 1000.0 / e2e_ms, "unit": "iter/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "input_pipeline": pipeline}
     clocks = sampler.stop() if rank == 0 else None
