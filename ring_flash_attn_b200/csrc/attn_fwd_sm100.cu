@@ -408,7 +408,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     if (n_rows > 0) {
       int xi = 0;
-      const bool stamper = (threadIdx.x & 127) == 0;
+      [[maybe_unused]] const bool stamper = (threadIdx.x & 127) == 0;  // RFA_TRACE builds only
       for (int si = 0; si < it.seg_count; ++si) {
         const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
         int seg_lo = 0;

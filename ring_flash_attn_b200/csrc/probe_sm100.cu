@@ -60,7 +60,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   uint8_t* sa = smem;             // up to 32 KB
   uint8_t* sb = smem + 32768;     // up to 32 KB
   Smem* sm = reinterpret_cast<Smem*>(smem + 65536);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, tid = threadIdx.x;
 
   if (tid == 0) {
     mbar_init(&sm->full, 1);
