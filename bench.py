@@ -134,6 +134,46 @@ def load_reference():
     return ring_flash_attn
 
 
+class PrefetchedE2E:
+    """The end-to-end step with the input pipeline every training loop has: while step i computes, the host->device
+    copy of step i+1's inputs (from the same pinned host tensors) runs on a side stream into the other half of a
+    double buffer.  Every step's inputs are still copied from pinned host memory inside the timed region (one copy
+    per timed step) and the loss is read back every step; only the serialisation of copy and compute is gone.
+    Used for both arms (RFA_BENCH_E2E_PREFETCH=0 restores the serial loop).
+
+    ``cuda`` is ``torch.cuda`` (a stand-in with the same five names in tests/test_bench_scripts.py)."""
+
+    def __init__(self, cuda, torch, dev, host_in, step, loss_host, needs_grad):
+        self.cuda, self.step, self.host_in, self.loss_host, self.needs_grad = cuda, step, host_in, loss_host, needs_grad
+        self.copy_stream = cuda.Stream(device=dev)
+        self.bufs = [[torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_in] for _ in range(2)]
+        self.ready = [cuda.Event(), cuda.Event()]
+        self.consumed = [cuda.Event(), cuda.Event()]
+        self.i = 0
+        self._prefetch(0)
+
+    def _prefetch(self, i):
+        b = i & 1
+        with self.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[b])  # the step that last read this half has finished
+            for d, h in zip(self.bufs[b], self.host_in):
+                d.copy_(h, non_blocking=True)
+            self.ready[b].record(self.copy_stream)
+
+    def __call__(self):
+        i, b = self.i, self.i & 1
+        self.i += 1
+        self._prefetch(i + 1)  # next step's inputs travel while this step computes
+        cur = self.cuda.current_stream()
+        cur.wait_event(self.ready[b])
+        ins = [d.detach().requires_grad_(self.needs_grad) for d in self.bufs[b]]
+        out = self.step(ins)
+        self.loss_host.copy_(out.float().mean().reshape(1), non_blocking=True)
+        self.consumed[b].record(cur)
+        cur.synchronize()
+        return float(self.loss_host[0])
+
+
 def main():
     args = parse()
     import torch
@@ -199,42 +239,6 @@ def main():
         torch.cuda.current_stream().synchronize()
         return float(loss_host[0])
 
-    class PrefetchedE2E:
-        """The same end-to-end step with the input pipeline every training loop has: while step i computes, the
-        host->device copy of step i+1's inputs (from the same pinned host tensors) runs on a side stream into
-        the other half of a double buffer.  Every step's inputs are still copied from pinned host memory inside
-        the timed region (one copy per timed step), and the loss is read back every step; only the serialisation
-        of copy and compute is gone.  Used for both arms (RFA_BENCH_E2E_PREFETCH=0 restores the serial loop)."""
-
-        def __init__(self):
-            self.copy_stream = torch.cuda.Stream(device=dev)
-            self.bufs = [[torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_in] for _ in range(2)]
-            self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-            self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
-            self.i = 0
-            self._prefetch(0)
-
-        def _prefetch(self, i):
-            b = i & 1
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(self.consumed[b])  # the step that last read this half has finished
-                for d, h in zip(self.bufs[b], host_in):
-                    d.copy_(h, non_blocking=True)
-                self.ready[b].record(self.copy_stream)
-
-        def __call__(self):
-            i, b = self.i, self.i & 1
-            self.i += 1
-            self._prefetch(i + 1)  # next step's inputs travel while this step computes
-            cur = torch.cuda.current_stream()
-            cur.wait_event(self.ready[b])
-            ins = [d.detach().requires_grad_(args.mode != "fwd") for d in self.bufs[b]]
-            out = step(ins)
-            loss_host.copy_(out.float().mean().reshape(1), non_blocking=True)
-            self.consumed[b].record(cur)
-            cur.synchronize()
-            return float(loss_host[0])
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -285,7 +289,7 @@ def main():
         run_e2e = e2e_step
         if os.environ.get("RFA_BENCH_E2E_PREFETCH", "1") == "1":
             try:
-                run_e2e = PrefetchedE2E()
+                run_e2e = PrefetchedE2E(torch.cuda, torch, dev, host_in, step, loss_host, args.mode != "fwd")
                 run_e2e()  # one untimed step proves the pipeline works on this box before it is timed
                 pipeline = "double-buffered prefetch on a side stream (copy of step i+1 under compute of step i)"
             except Exception as exc:  # noqa: BLE001 - never lose the benchmark line over the input pipeline

@@ -37,3 +37,64 @@ def test_bench_reference_arm_reports_unavailable_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_prefetched_e2e_loop_pipelines_one_copy_per_step():
+    """bench.PrefetchedE2E with synchronous stand-ins for torch.cuda: step i must consume exactly the inputs that
+    were on the host when step i-1 ran (copied while step i-1 'computed'), from alternating buffers, one host->device
+    copy per step."""
+    import contextlib
+    import importlib.util
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    log = []
+
+    class Event:
+        def record(self, stream=None):
+            log.append("record")
+
+    class Stream:
+        def __init__(self, device=None):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def synchronize(self):
+            pass
+
+    _Event, _Stream = Event, Stream
+
+    class Cuda:
+        Event, Stream = _Event, _Stream
+
+        @staticmethod
+        @contextlib.contextmanager
+        def stream(s):
+            yield
+
+        @staticmethod
+        def current_stream():
+            return Stream()
+
+    host = [torch.zeros(4)]
+    seen = []
+
+    def step(ins):
+        seen.append((float(ins[0][0]), ins[0].data_ptr()))
+        return ins[0] * 1.0
+
+    loss_host = torch.zeros(1)
+    e2e = bench.PrefetchedE2E(Cuda, torch, torch.device("cpu"), host, step, loss_host, False)
+    for i in range(5):
+        host[0].fill_(float(i + 1))  # what the "data loader" holds while step i runs = inputs of step i+1
+        loss = e2e()
+        assert loss == float(i)  # step i sees the value the host held one call earlier (0 at construction)
+    assert [v for v, _ in seen] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    ptrs = [p for _, p in seen]
+    assert ptrs[0] == ptrs[2] == ptrs[4] and ptrs[1] == ptrs[3] and ptrs[0] != ptrs[1]  # double buffer alternates
