@@ -61,3 +61,17 @@ def quantize_blockwise(x: torch.Tensor, block: Sequence[int], dtype: torch.dtype
     descale = amax / fmax
     q = (x.float() / _expand_scale(descale, x.shape)).clamp(-fmax, fmax).to(dtype)
     return q, descale
+
+
+def quantize_per_head(x: torch.Tensor, keep_dims: Sequence[int] = (), dtype: torch.dtype = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One descale per head (heads at dim -2), plus one per index of every dim listed in ``keep_dims`` (e.g. the
+    pack dim of a kv / qkv tensor).  This is the granularity the fp8 forward kernel consumes natively
+    (``RFA_B200_FP8_KERNEL=1``); finer block scales are dequantised to bf16 in front of the kernels.
+
+        q8, dq = quantize_per_head(q)                       # q (B, S, H, D)       -> dq (1, 1, H, 1)
+        kv8, dkv = quantize_per_head(kv, keep_dims=(2,))    # kv (B, S, 2, Hkv, D) -> dkv (1, 1, 2, Hkv, 1)
+    """
+    nd = x.dim()
+    keep = {d % nd for d in keep_dims} | {nd - 2}
+    return quantize_blockwise(x, [1 if d in keep else 0 for d in range(nd)], dtype)
+

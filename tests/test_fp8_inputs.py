@@ -88,3 +88,21 @@ def test_fp8_kernel_opt_in_is_ignored_off_gpu(monkeypatch):
     assert api._per_head(torch.tensor(2.0), x).tolist() == [2.0] * 4
     assert api._per_head(torch.arange(4.0).view(1, 1, 4, 1), x).tolist() == [0.0, 1.0, 2.0, 3.0]
     assert api._per_head(torch.ones(1, 2, 4, 1), x) is None  # token-block scales: not per-head
+
+
+def test_quantize_per_head_shapes_and_roundtrip():
+    from ring_flash_attn_b200.parallel import api
+    from ring_flash_attn_b200.utils import fp8
+
+    torch.manual_seed(0)
+    q = torch.randn(2, 16, 4, 128)
+    kv = torch.randn(2, 16, 2, 2, 128)
+    q8, dq = fp8.quantize_per_head(q)
+    kv8, dkv = fp8.quantize_per_head(kv, keep_dims=(2,))
+    assert dq.shape == (1, 1, 4, 1) and dkv.shape == (1, 1, 2, 2, 1)
+    assert (fp8.dequantize(q8, dq, torch.float32) - q).abs().max() < 0.07 * q.abs().max()
+    # exactly the granularity the kernel path accepts
+    assert api._per_head(dq, q8) is not None
+    dk, dv = api._split_descale(dkv, 2, 2)
+    assert api._per_head(dk, kv8[:, :, 0]) is not None and api._per_head(dv, kv8[:, :, 1]) is not None
+
