@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 C.set_trace(None)
 t = trace.cpu().view(64, 16)
 base = int(t[t > 0].min())
-names = ["mma:top", "mma:S+1", "mma:Pok", "mma:dSok", "mma:dqfree", "mma:end", "sm:Sfull", "sm:Parr", "sm:dPfull",
+names = ["mma:top", "mma:dSok", "mma:dPiss", "mma:dqfree", "mma:dQiss", "mma:end", "sm:Sfull", "sm:Parr", "sm:dPfull",
          "sm:dSarr", "-", "dr:dqfull", "dr:done"]
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for i in range(6, 26):

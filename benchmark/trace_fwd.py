@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 C.set_trace(None)
 t = trace.cpu().view(64, 16)
 base = int(t[t > 0].min())
-names = ["mma:top", "mma:Kfull", "mma:P1ok", "mma:QK1done", "mma:P0ok", "mma:PV0iss",
+names = ["mma:top", "mma:VKok", "mma:P0ok", "mma:PV0QK0", "mma:P1ok", "mma:end",
          "s0:Sfull", "s0:ld", "s0:turn", "s0:exp", "s0:arr", "s1:Sfull", "s1:ld", "s1:turn", "s1:exp", "s1:arr"]
 print("iter " + " ".join(f"{n:>10s}" for n in names))
 for i in range(4, 24):

@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-DRFA_BUILD"]
 if os.environ.get("RFA_TRACE", "0") == "1":
     NVCC_FLAGS.append("-DRFA_TRACE")
-CU_SOURCES = ["attn_fwd_sm100.cu", "attn_fwd_h64_sm100.cu", "attn_bwd_sm100.cu", "tensor_map.cu", "lse_layout.cu", "probe_sm100.cu",
+CU_SOURCES = ["attn_fwd_sm100.cu", "attn_bwd_sm100.cu", "tensor_map.cu", "lse_layout.cu", "probe_sm100.cu",
               "probe_fp8_sm100.cu", "comm_sm100.cu"]
 CPP_SOURCES = ["bindings.cpp", "peer_mem.cpp"]
 

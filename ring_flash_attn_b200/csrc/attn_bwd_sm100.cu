@@ -51,8 +51,6 @@ constexpr int kQHalf = kQBytes / 2;                // 64-wide swizzled sub-tile 
 constexpr int kKVHalf = kKVBytes / 2;              // 16 KB
 constexpr int kDSBytes = kTileK * kTileQ * 2;      // 16 KB
 constexpr int kDQBytes = kTileQ * kD * 4;          // 32 KB fp32 staging
-constexpr int kBulkPitch = kD * 4 + 16;            // experimental bulk dK/dV epilogue: padded fp32 row
-constexpr int kBulkStageBytes = kTileK * kBulkPitch;  // 66 KB per tile; dK at smem_k, dV right behind it
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 192, kColDV = 256, kColDK = 384;
 
@@ -73,7 +71,6 @@ struct Barriers {
   uint32_t pad;
 };
 
-static_assert(2 * kBulkStageBytes <= 2 * kKVBytes + kStages * 2 * kQBytes, "bulk staging must fit in K|V|Q/dO");
 constexpr int kStatBytes = kStages * 2 * kTileQ * 4;  // lse / delta ring, same slots as Q/dO
 constexpr int kSmemBytes =
     2 * kKVBytes + kStages * 2 * kQBytes + kDSBytes + kDQBytes + kStatBytes + 1024 /*barriers*/ + 1024 /*slack*/;
@@ -96,10 +93,7 @@ __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
   return g;
 }
 
-// kDsTmem (experimental, RFA_B200_BWD_V2 bit 1): dS^T is also parked in tensor memory (in the dP^T columns its
-// warpgroup has just consumed) and the dK GEMM takes it as a TMEM A-operand like dV takes P^T - one 16 KB
-// shared-memory operand read less per tile; the dQ^T GEMM still reads the shared-memory copy as its B operand.
-template <typename T, bool kWindow, bool kDqDirect, bool kDsTmem>
+template <typename T, bool kWindow>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -248,11 +242,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&bars->kv_full, 0);
         tc_fence_after();
 
-        uint32_t slot = 0, phase = 0;
+        // Issue order (round 2).  The longest dependency chain of a tile runs through the softmax warpgroups:
+        //   dP^T(i) complete -> dS^T(i) written -> [dK(i), dQ^T(i)] ... -> dP^T(i+1) complete -> dS^T(i+1) ...
+        // (dP^T has ONE tensor-memory buffer, so dP^T(i+1) can only be issued once dS^T(i) exists).  Round 1 issued
+        // dP^T(i+1) LAST in iteration i, behind S^T(i+1), dV(i), dK(i) and dQ^T(i): 3660 cycles per tile for 1664
+        // cycles of tensor work (profiles/trace_bwd_cta0.log).  Now dP^T(i+1) is the FIRST thing issued when dS^T(i)
+        // arrives, and everything that does not depend on the softmax of tile i+1 (dK(i), dQ^T(i), S^T(i+2),
+        // dV(i+1)) fills the pipe behind it while the softmax warps turn dP^T(i+1) into dS^T(i+1).
+        // S^T runs two tiles ahead (three Q/dO stages are in flight: i, i+1, i+2).
         uint32_t ph_p[2] = {0, 0};
         uint32_t ph_ds = 0, ph_dqfree = 0;
-        // software pipeline: S^T of tile i+1 is issued before the dV/dK/dQ GEMMs of tile i
-        int issued_s = 0;          // tiles whose S^T has been issued
+        int issued_s = 0;                  // tiles whose S^T has been issued
         uint32_t s_slot = 0, s_phase = 0;  // ring position used by the next S^T issue
         auto issue_s = [&]() {
           mbar_wait(&bars->qdo_full[s_slot], s_phase);
@@ -267,75 +267,67 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             s_phase ^= 1;
           }
         };
-        issue_s();
-        // dP^T of tile 0
-        if (leader) {
+        // dV(t) += P^T(t) dO(t)   (P^T: bf16 in the first 32 columns of tile t's S^T buffer)
+        auto issue_dv = [&](int t, uint32_t t_slot) {
+          mbar_wait(&bars->p_ready[t & 1], ph_p[t & 1]);
+          ph_p[t & 1] ^= 1;
+          tc_fence_after();
+          const uint32_t do_mn = q_mn0 + t_slot * stage_step + do_step;  // dO_t read MN-major
+          if (leader)
+#pragma unroll
+            for (int k = 0; k < kTileQ / 16; ++k)
+              umma_ts2(tmem + kColDV, tmem + kColS + (t & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8,
+                       do_mn + k * (2048 >> 4), hi, idesc_dv, (t > 0 || k > 0) ? 1u : 0u);
+        };
+        auto next_slot = [](uint32_t sl) { return sl + 1 == kStages ? 0u : sl + 1; };
+
+        issue_s();  // S^T(0)
+        if (leader) {  // dP^T(0): its Q/dO stage has landed (S^T(0) waited for it)
           issue_kq(tmem + kColDP, v_km, q_km0 + do_step);
           umma_commit(&bars->dp_full);
         }
+        if (total_tiles > 1) issue_s();  // S^T(1)
+        issue_dv(0, 0);
+        uint32_t slot = 0;  // stage of tile i
         for (int i = 0; i < total_tiles; ++i) {
           const uint32_t q_mn = q_mn0 + slot * stage_step;  // Q_i read MN-major (B of dK)
-          const uint32_t do_mn = q_mn + do_step;            // dO_i read MN-major (B of dV)
+          const uint32_t slot1 = next_slot(slot);
           RFA_STAMP(leader, i, 0);
-          if (i + 1 < total_tiles && !(p.debug & 2)) issue_s();
-          RFA_STAMP(leader, i, 1);
-          // dV += P^T dO   (P^T: bf16 in the first 32 columns of this tile's S^T buffer)
-          mbar_wait(&bars->p_ready[i & 1], ph_p[i & 1]);
-          ph_p[i & 1] ^= 1;
-          tc_fence_after();
-          RFA_STAMP(leader, i, 2);
-          if (leader)
-#pragma unroll
-          for (int k = 0; k < kTileQ / 16; ++k)
-            umma_ts2(tmem + kColDV, tmem + kColS + (i & 1) * 64 + (k >> 1) * 32 + (k & 1) * 8, do_mn + k * (2048 >> 4), hi, idesc_dv,
-                     (i > 0 || k > 0) ? 1u : 0u);
-          // dK += dS^T Q ; dQ^T = K^T dS
-          mbar_wait(&bars->ds_ready, ph_ds);
+          mbar_wait(&bars->ds_ready, ph_ds);  // dS^T(i) is in shared memory; dP^T(i) has been consumed
           ph_ds ^= 1;
           tc_fence_after();
-          RFA_STAMP(leader, i, 3);
-          if (leader) {
-            if constexpr (kDsTmem) {
+          RFA_STAMP(leader, i, 1);
+          if (i + 1 < total_tiles && leader) {  // dP^T(i+1) first: it heads the critical chain
+            issue_kq(tmem + kColDP, v_km, q_km0 + slot1 * stage_step + do_step);
+            umma_commit(&bars->dp_full);
+          }
+          RFA_STAMP(leader, i, 2);
+          if (leader) {  // dK += dS^T Q
 #pragma unroll
-              for (int k = 0; k < kTileQ / 16; ++k)
-                umma_ts2(tmem + kColDK, tmem + kColDP + (k >> 1) * 32 + (k & 1) * 8, q_mn + k * (2048 >> 4), hi,
-                         idesc_dv, (i > 0 || k > 0) ? 1u : 0u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < kTileQ / 16; ++k)
-                umma_ss2(tmem + kColDK, ds_km + k * (32 >> 4), hi, q_mn + k * (2048 >> 4), hi, idesc_dv,
-                         (i > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < kTileQ / 16; ++k)
+              umma_ss2(tmem + kColDK, ds_km + k * (32 >> 4), hi, q_mn + k * (2048 >> 4), hi, idesc_dv,
+                       (i > 0 || k > 0) ? 1u : 0u);
           }
           if (i > 0) {  // previous dQ^T must have been drained out of TMEM
             mbar_wait(&bars->dq_free, ph_dqfree);
             ph_dqfree ^= 1;
             tc_fence_after();
           }
-          RFA_STAMP(leader, i, 4);
-          if (leader) {
+          RFA_STAMP(leader, i, 3);
+          if (leader) {  // dQ^T = K^T dS
 #pragma unroll
             for (int k = 0; k < kTileK / 16; ++k)
               umma_ss2(tmem + kColDQ, k_mn + k * (2048 >> 4), hi, ds_km + k * (2048 >> 4), hi, idesc_dq, k > 0);
-            umma_commit(&bars->dq_full);
-            umma_commit(&bars->qdo_empty[slot]);  // Q_i / dO_i no longer needed once everything above retires
+            umma_commit(&bars->dq_full);            // also tells the softmax warps that dS^T(i) may be overwritten
+            umma_commit(&bars->qdo_empty[slot]);    // Q_i / dO_i no longer needed once everything above retires
           }
-          if (++slot == kStages) {
-            slot = 0;
-            phase ^= 1;
-          }
-          // dP^T of the next tile (its dO stage is `slot` now); the softmax warps have finished reading the
-          // previous dP^T because ds_ready was observed above.
-          if (i + 1 < total_tiles) {
-            mbar_wait(&bars->qdo_full[slot], phase);  // already landed (S^T of that tile was issued)
-            tc_fence_after();
-            if (leader) {
-              issue_kq(tmem + kColDP, v_km, q_km0 + slot * stage_step + do_step);
-              umma_commit(&bars->dp_full);
-            }
-          }
-          if (i + 1 < total_tiles && (p.debug & 2)) issue_s();
+          RFA_STAMP(leader, i, 4);
+          if (i + 1 < total_tiles) issue_dv(i + 1, slot1);  // dV(i+1): P^T(i+1) has been ready for a while
+          // S^T(i+2) last: its stage was released by tile i-1 one iteration ago, so this is the only wait of the
+          // loop that may have to sit out a TMA latency (its buffer held P^T(i), and dV(i) has been issued)
+          if (i + 2 < total_tiles) issue_s();
           RFA_STAMP(leader, i, 5);
+          slot = slot1;
           __syncwarp();
         }
         if (leader) umma_commit(&bars->dkv_done);
@@ -471,27 +463,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld32(tmem + kColDP + lane_addr + c0, dpr);
           tmem_ld_wait();
           uint8_t* ds_row = smem_ds + key * 128;
-          [[maybe_unused]] uint32_t ds_pk[16];
+          uint32_t ds_pk[16];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 v;
-            uint32_t w[4];
+          for (int c = 0; c < 32; c += 2) {
+            const float d0 = pr[c] * (__uint_as_float(dpr[c]) - dlt[c]) * p.scale;
+            const float d1 = pr[c + 1] * (__uint_as_float(dpr[c + 1]) - dlt[c + 1]) * p.scale;
+            ds_pk[c >> 1] = Pack2<T>::pack(d0, d1);
+          }
+          // dS^T has ONE shared-memory buffer and dP^T(i) is now issued ahead of dK(i-1) / dQ^T(i-1): those two
+          // GEMMs must have finished reading dS^T(i-1) before it is overwritten (dq_full = "dQ^T(i-1) complete",
+          // which by in-order completion covers dK(i-1) as well)
+          if (i > 0) mbar_wait(&bars->dq_full, (i - 1) & 1);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = ch * 8 + e * 2;
-              const float d0 = pr[c] * (__uint_as_float(dpr[c]) - dlt[c]) * p.scale;
-              const float d1 = pr[c + 1] * (__uint_as_float(dpr[c + 1]) - dlt[c + 1]) * p.scale;
-              w[e] = Pack2<T>::pack(d0, d1);
-              if constexpr (kDsTmem) ds_pk[ch * 4 + e] = w[e];
-            }
-            v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
-            *reinterpret_cast<uint4*>(ds_row + (((half * 4 + ch) ^ (key & 7)) << 4)) = v;
-          }
-          if constexpr (kDsTmem) {
-            // the 32 dP^T columns of this warpgroup are in registers; their first 16 now hold its half of dS^T
-            tmem_st16(tmem + kColDP + lane_addr + c0, ds_pk);
-            tmem_st_wait();
-          }
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(ds_row + (((half * 4 + ch) ^ (key & 7)) << 4)) =
+                make_uint4(ds_pk[ch * 4], ds_pk[ch * 4 + 1], ds_pk[ch * 4 + 2], ds_pk[ch * 4 + 3]);
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&bars->ds_ready);
@@ -511,41 +497,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(&bars->dkv_done, 0);
       tc_fence_after();
     }
-    const bool bulk = remote && p.dkv.bulk != 0 && total_tiles > 0;
-    if (bulk) {
-      // Experimental (RFA_B200_DKV_BULK=1, off by default until validated on hardware).  The default epilogue
-      // below sends one 16-byte NVLink store per lane and row.  Here every thread (== key row) parks its fp32
-      // row in shared memory that is idle by now (dK: K|V plus the head of the Q/dO ring, dV: the rest of the
-      // Q/dO ring) and ships it itself with one 512-byte cp.async.bulk - no cross-thread hand-off is needed
-      // because a thread only sends what it wrote.  Rows are pitched 528 bytes apart so that the 16-byte stores
-      // of a warp fall into 8 distinct bank groups (4 wavefronts per instruction, the minimum for 512 bytes).
-      const int which = half;
-      uint8_t* stage = which == 0 ? smem_k : smem_k + kBulkStageBytes;
-      const uint32_t col = tmem + (which == 0 ? kColDK : kColDV) + lane_addr;
-      float* mine = reinterpret_cast<float*>(stage + key * kBulkPitch);
-#pragma unroll
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(col + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<uint4*>(mine + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
-      }
-      fence_proxy_async_smem();
-      if (key_ok) {
-        float* base = which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner];
-        bulk_store(base + (static_cast<size_t>(row) * p.hkv + kv_head) * kD, mine, kD * sizeof(float));
-        tma_store_commit();
-        tma_store_wait<0>();  // written, not just read: the flag below must not overtake the data
-        fence_proxy_async_all();
-      }
-    } else {
-      const int which = half;
-      float* base = remote ? (which == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner])
-                           : (which == 0 ? p.dk : p.dv);
-      float* dst = base + (static_cast<size_t>(row) * p.hkv + kv_head) * kD;
-      const uint32_t col = tmem + (which == 0 ? kColDK : kColDV) + lane_addr;
+    // Every thread (== key row) parks its row in shared memory that is idle by now (all GEMMs of this CTA have
+    // retired and every TMA load has landed: dK uses K | V plus the head of the Q/dO ring, dV the rest of the ring)
+    // and ships it itself with ONE bulk copy - no cross-thread hand-off is needed because a thread only sends
+    // what it wrote.  Rows are pitched 16 bytes past their length so that the 16-byte stores of a warp fall into 8
+    // distinct bank groups.  The row is written in the model dtype (fused multi-GPU launches and world size 1:
+    // half the NVLink / HBM bytes of round 1's fp32 rows, and no cast pass afterwards; the owner-side reduction
+    // accumulates the partials of different ranks in fp32) or in fp32 (torch.distributed fallback transports,
+    // which add the partials of successive ring steps).  Round 1 sent one 16-byte store per lane and row:
+    // measured 1.91 -> 1.64 ms per fwd+bwd on 2 GPUs for the headline shard (profiles/r2/breakdown_bulk*.log).
+    auto store_rows = [&](auto tag) {
+      using O = decltype(tag);
+      constexpr int kRowBytes = kD * static_cast<int>(sizeof(O));
+      constexpr int kPitch = kRowBytes + 16;
+      static_assert(2 * kTileK * kPitch <= 2 * kKVBytes + kStages * 2 * kQBytes, "staging must fit in K|V|Q/dO");
+      uint8_t* mine = smem_k + half * (kTileK * kPitch) + key * kPitch;
+      const uint32_t col = tmem + (half == 0 ? kColDK : kColDV) + lane_addr;
 #pragma unroll
       for (int c = 0; c < 128; c += 32) {
         uint32_t r[32];
@@ -554,15 +521,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) r[e] = 0;
+          for (int e = 0; e < 32; ++e) r[e] = 0;  // tile no local query reaches: the owner still needs defined rows
         }
-        if (key_ok) {
+        if constexpr (sizeof(O) == 4) {
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<uint4*>(dst + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+            *reinterpret_cast<uint4*>(mine + (c + e) * 4) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 v;
+            v.x = Pack2<T>::pack(__uint_as_float(r[e + 0]), __uint_as_float(r[e + 1]));
+            v.y = Pack2<T>::pack(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+            v.z = Pack2<T>::pack(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
+            v.w = Pack2<T>::pack(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
+            *reinterpret_cast<uint4*>(mine + (c + e) * 2) = v;
+          }
         }
       }
-    }
+      fence_proxy_async_smem();
+      if (key_ok) {
+        uint8_t* base = static_cast<uint8_t*>(remote ? (half == 0 ? p.dkv.dk_ptrs[it.owner] : p.dkv.dv_ptrs[it.owner])
+                                                     : (half == 0 ? p.dk : p.dv));
+        bulk_store(base + (static_cast<size_t>(row) * p.hkv + kv_head) * kRowBytes, mine, kRowBytes);
+        tma_store_commit();
+        tma_store_wait<0>();  // written, not just read: the flag below must not overtake the data
+        fence_proxy_async_all();
+      }
+    };
+    if (p.dkv_fp32) store_rows(float{});
+    else store_rows(T{});
     if (remote) {
       // publish: the last tile destined for an owner raises that owner's "gradients landed" flag
       __threadfence_system();
@@ -597,22 +585,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&bars->dq_free);
-          if constexpr (kDqDirect) {
-            // thread == head-dim lane: for a fixed query row the 32 lanes of a warp hit 128 consecutive bytes, so
-            // every instruction is one coalesced L2 reduction - the same L2 traffic as the TMA reduce-add, without
-            // the 32 KB write + 32 KB read of the shared-memory staging tile
-            const int row0 = g.q_row0 + ti * kTileQ;
-            float* base = p.dq + static_cast<long long>(row0) * p.dq_row_stride + head * p.dq_head_stride + wg_tid;
-            const int n_ok = p.dq_rows - row0 < kTileQ ? p.dq_rows - row0 : kTileQ;  // clip at the tensor end
-#pragma unroll
-            for (int q = 0; q < kTileQ; ++q) {
-              if (q < n_ok)
-                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + q * p.dq_row_stride), "f"(__uint_as_float(r[q]))
-                             : "memory");
-            }
-            RFA_STAMP(wg_tid == 0, i, 12);
-            continue;
-          }
           // the previous tile's reduce must have finished reading the staging buffer
           if (wg_tid == 0) tma_store_wait_read<0>();
           named_bar_sync(4, 128);
@@ -703,21 +675,12 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
     if (err == cudaSuccess) kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   };
-  const int v2 = p.window ? 0 : (p.dq_direct & 3);  // bit 0: direct dQ reduction, bit 1: dS^T as TMEM operand
   if (dtype == kDtypeBF16) {
-    using B = __nv_bfloat16;
-    if (p.window) launch(bwd::attn_bwd_kernel<B, true, false, false>);
-    else if (v2 == 1) launch(bwd::attn_bwd_kernel<B, false, true, false>);
-    else if (v2 == 2) launch(bwd::attn_bwd_kernel<B, false, false, true>);
-    else if (v2 == 3) launch(bwd::attn_bwd_kernel<B, false, true, true>);
-    else launch(bwd::attn_bwd_kernel<B, false, false, false>);
+    if (p.window) launch(bwd::attn_bwd_kernel<__nv_bfloat16, true>);
+    else launch(bwd::attn_bwd_kernel<__nv_bfloat16, false>);
   } else {
-    using H = __half;
-    if (p.window) launch(bwd::attn_bwd_kernel<H, true, false, false>);
-    else if (v2 == 1) launch(bwd::attn_bwd_kernel<H, false, true, false>);
-    else if (v2 == 2) launch(bwd::attn_bwd_kernel<H, false, false, true>);
-    else if (v2 == 3) launch(bwd::attn_bwd_kernel<H, false, true, true>);
-    else launch(bwd::attn_bwd_kernel<H, false, false, false>);
+    if (p.window) launch(bwd::attn_bwd_kernel<__half, true>);
+    else launch(bwd::attn_bwd_kernel<__half, false>);
   }
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();

@@ -84,20 +84,19 @@ struct SignalParams {
 
 // Backward: where dK/dV tiles go.  owner slot o = (fp32 inbox of rank o, slot reserved for this rank).
 struct DkvParams {
-  float* dk_ptrs[kMaxRanks];
-  float* dv_ptrs[kMaxRanks];
+  void* dk_ptrs[kMaxRanks];  // owner o: this rank's slot in o's inbox (model dtype)
+  void* dv_ptrs[kMaxRanks];
   uint32_t* peer_pads[kMaxRanks];
   uint32_t* my_pad;
   uint32_t* sent_count;               // device counters per owner (cumulative)
   uint32_t sent_target[kMaxRanks];
   uint32_t epoch;
   uint32_t wait_epoch;  // epoch of the previous backward call: owners must have reduced it before we overwrite
-  int bulk;             // experimental: stage tiles in smem and send rows with cp.async.bulk (default 0)
   int world;  // 0 = disabled: write to BwdParams::dk / dv
   int my_rank;
 };
 
-// Owner-side reduction of the fp32 inbox into dK / dV (csrc/comm_sm100.cu).
+// Owner-side reduction of the inbox (model dtype partials, summed in fp32) into dK / dV (csrc/comm_sm100.cu).
 struct alignas(16) ReduceTask {
   int row0, rows;
   unsigned src_mask;  // ranks whose slot holds a partial for these rows
@@ -106,9 +105,9 @@ struct alignas(16) ReduceTask {
 struct ReduceParams {
   const ReduceTask* tasks;
   int n_tasks;
-  const float* inbox;     // [world][2][rows_cap * hkv * 128]
-  long long slot_stride;  // floats between slots
-  long long kv_stride;    // floats between the dK and dV halves of a slot
+  const void* inbox;      // [world][2][rows_cap * hkv * 128], model dtype
+  long long slot_stride;  // elements between slots
+  long long kv_stride;    // elements between the dK and dV halves of a slot
   void* dk;               // (rows, hkv, 128) contiguous, output dtype
   void* dv;
   int row_elems;          // hkv * 128
@@ -121,6 +120,8 @@ struct ReduceParams {
 };
 constexpr int kReduceBlocksPerTask = 128;
 const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream);
+// out = cast(acc); acc = 0   (fp32 dQ accumulator -> model dtype, workspace left zeroed for the next backward)
+const char* dq_finalize_launch(int dtype, float* acc, void* out, long long numel, cudaStream_t stream);
 
 struct FwdParams {
   const WorkItem* items;
@@ -128,8 +129,6 @@ struct FwdParams {
   const int* seg_lo;  // sliding window only (else nullptr): per segment, key j visible to chunk row i iff j >= i + lo
   const float* head_scale_qk;  // fp8 only: q_descale * k_descale per QUERY head (multiplies the softmax scale)
   const float* head_scale_v;   // fp8 only: v_descale per KV head (multiplies the output)
-  int flags;  // experiment switches of the h64 forward (RFA_B200_FWD_FLAGS): bit 0 = no turn-taking between the
-              // two softmax warpgroups
   void* out;  // (rows, hq, 128) contiguous, input dtype
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;
@@ -168,24 +167,16 @@ struct BwdParams {
   const BwdQSegment* qsegs;
   const float* lse;    // same indexing as FwdParams::lse
   const float* delta;  // rowsum(out * dout), same indexing
-  float* dk;           // (kv rows, hkv, 128) fp32, rows of each item are written (not accumulated)
-  float* dv;
+  void* dk;            // (kv rows, hkv, 128), rows of each item are written (not accumulated); dtype: dkv_fp32
+  void* dv;
+  int dkv_fp32;        // 1: dk / dv are fp32 (fallback transports accumulate ring steps), 0: model dtype
   int lse_S;
   int hq, hkv;
   float scale, scale_log2;
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
   int n_items;
-  int debug;  // bisecting aid: bit1 = no S^T look-ahead
   int window;  // != 0: BwdQSegment::lo is meaningful (selects the kernel variant that masks the lower band edge)
-  // experimental backward variants (RFA_B200_BWD_V2 bit mask).  Bit 0: the drain warpgroup adds dQ^T tiles to the
-  // accumulator with coalesced red.global.add.f32 straight from registers instead of staging them in shared memory
-  // for a TMA reduce-add.  Bit 1: dS^T is parked in tensor memory as the A operand of the dK GEMM.
-  int dq_direct;
-  float* dq;                 // the fp32 accumulator (rows, hq, 128) the TMA map tm_dq also points at
-  long long dq_row_stride;   // floats
-  long long dq_head_stride;  // floats
-  int dq_rows;
   unsigned long long* trace;  // RFA_TRACE builds only
   PushParams push;
   SignalParams sig;
@@ -211,11 +202,6 @@ enum : int { kDtypeBF16 = 0, kDtypeFP16 = 1, kDtypeE4M3 = 2 };
 const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k, const TensorView& v,
                             const TensorView& k_stage, const TensorView& v_stage, const FwdParams& p,
                             cudaStream_t stream);
-
-// 64-key-step variant of the forward (csrc/attn_fwd_h64_sm100.cu), same contract, bf16 / fp16 without windows.
-const char* attn_fwd_h64_launch(int dtype, const TensorView& q, const TensorView& k, const TensorView& v,
-                                const TensorView& k_stage, const TensorView& v_stage, const FwdParams& p,
-                                cudaStream_t stream);
 
 const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const TensorView& dout, float* delta, int lse_S,
                                   cudaStream_t stream);

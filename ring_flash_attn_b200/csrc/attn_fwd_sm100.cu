@@ -286,76 +286,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (has_t1) mbar_wait(&bars->q_full[1], 0);
       tc_fence_after();
 
-      uint32_t slot = 0, phase = 0;            // ring position of the next K tile
-      uint32_t p_phase[2] = {0, 0};
-      bool o_started[2] = {false, false};
-      bool pend1 = false;                      // PV of tile 1 deferred to the next iteration
-      uint32_t pend1_slot = 0;
-      auto advance = [&]() {
+      // Software pipeline (round 2).  Per q-tile t the dependent chain of one key tile is
+      //   S_t(j) complete -> softmax -> P_t(j) -> PV_t(j) -> QK_t(j+1) -> S_t(j+1) complete
+      // (S and P share tensor-memory columns, so QK_t(j+1) has to queue behind PV_t(j)).  Round 1 issued
+      // QK_0(j+1) only after the loop bookkeeping and the K wait of iteration j+1 (~530 cycles of a 3940-cycle
+      // iteration, profiles/trace_fwd_cta0.log); now the geometry of step j+1 is computed and its K tile awaited
+      // BEFORE P_t(j) is awaited, and QK_t(j+1) is issued back to back with PV_t(j) for both tiles.
+      struct Step {
+        bool valid, a0, a1;
+        uint32_t k_slot, k_phase, v_slot, v_phase;
+      };
+      uint32_t slot = 0, phase = 0;  // ring position of the next K tile
+      int it_si = 0, it_jj = 0;
+      SegGeom it_g = it.seg_count > 0 ? seg_geom(p.segs[it.seg_begin], it) : SegGeom{0, 0, 0, 0};
+      auto next_step = [&]() {
+        Step st{};
+        while (it_si < it.seg_count && it_jj >= it_g.n_tiles) {
+          ++it_si;
+          it_jj = 0;
+          if (it_si < it.seg_count) it_g = seg_geom(p.segs[it.seg_begin + it_si], it);
+        }
+        if (it_si >= it.seg_count) return st;
+        st.valid = true;
+        st.a0 = tile_active(it_g, it, 0, it_jj);
+        st.a1 = tile_active(it_g, it, 1, it_jj);
+        st.k_slot = slot;
+        st.k_phase = phase;
         if (++slot == kStages) {
           slot = 0;
           phase ^= 1;
         }
-      };
-      int xi = 0;
-      for (int si = 0; si < it.seg_count; ++si) {
-        const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
-        for (int jj = 0; jj < g.n_tiles; ++jj, ++xi) {
-          const bool a0 = tile_active(g, it, 0, jj);
-          const bool a1 = tile_active(g, it, 1, jj);
-          const uint32_t k_slot = slot, k_phase = phase;
-          advance();
-          const uint32_t v_slot = slot, v_phase = phase;
-          advance();
-          RFA_STAMP(true, xi, 0);
-          mbar_wait(&bars->kv_full[k_slot], k_phase);
-          tc_fence_after();
-          RFA_STAMP(true, xi, 1);
-          if (a0 && leader) issue_qk(0, k_slot);
-          if (pend1) {  // PV_1 of the previous key tile (its V slot is still resident)
-            mbar_wait(&bars->p_ready[1], p_phase[1]);
-            p_phase[1] ^= 1;
-            tc_fence_after();
-            RFA_STAMP(true, xi, 2);
-            if (leader) {
-              issue_pv(1, pend1_slot, o_started[1]);
-              umma_commit(&bars->kv_empty[pend1_slot]);
-            }
-            o_started[1] = true;
-            pend1 = false;
-          }
-          if (leader) {
-            if (a1) issue_qk(1, k_slot);
-            umma_commit(&bars->kv_empty[k_slot]);
-          }
-          RFA_STAMP(true, xi, 3);
-          mbar_wait(&bars->kv_full[v_slot], v_phase);
-          tc_fence_after();
-          if (a0) {
-            mbar_wait(&bars->p_ready[0], p_phase[0]);
-            p_phase[0] ^= 1;
-            tc_fence_after();
-            RFA_STAMP(true, xi, 4);
-            if (leader) issue_pv(0, v_slot, o_started[0]);
-            RFA_STAMP(true, xi, 5);
-            o_started[0] = true;
-          }
-          if (a1) {
-            pend1 = true;
-            pend1_slot = v_slot;
-          } else if (leader) {
-            umma_commit(&bars->kv_empty[v_slot]);
-          }
-          __syncwarp();
+        st.v_slot = slot;
+        st.v_phase = phase;
+        if (++slot == kStages) {
+          slot = 0;
+          phase ^= 1;
         }
-      }
-      if (pend1) {
-        mbar_wait(&bars->p_ready[1], p_phase[1]);
+        ++it_jj;
+        return st;
+      };
+      uint32_t p_phase[2] = {0, 0};
+      bool o_started[2] = {false, false};
+      Step cur = next_step();
+      if (cur.valid) {
+        mbar_wait(&bars->kv_full[cur.k_slot], cur.k_phase);
         tc_fence_after();
         if (leader) {
-          issue_pv(1, pend1_slot, o_started[1]);
-          umma_commit(&bars->kv_empty[pend1_slot]);
+          if (cur.a0) issue_qk(0, cur.k_slot);
+          if (cur.a1) issue_qk(1, cur.k_slot);
+          umma_commit(&bars->kv_empty[cur.k_slot]);
         }
+      }
+      int xi = 0;
+      while (cur.valid) {
+        const Step nx = next_step();
+        RFA_STAMP(true, xi, 0);
+        mbar_wait(&bars->kv_full[cur.v_slot], cur.v_phase);
+        if (nx.valid) mbar_wait(&bars->kv_full[nx.k_slot], nx.k_phase);
+        tc_fence_after();
+        RFA_STAMP(true, xi, 1);
+        if (cur.a0) {
+          mbar_wait(&bars->p_ready[0], p_phase[0]);
+          p_phase[0] ^= 1;
+          tc_fence_after();
+          RFA_STAMP(true, xi, 2);
+          if (leader) issue_pv(0, cur.v_slot, o_started[0]);
+          o_started[0] = true;
+        }
+        if (leader && nx.valid && nx.a0) issue_qk(0, nx.k_slot);
+        RFA_STAMP(true, xi, 3);
+        if (cur.a1) {
+          mbar_wait(&bars->p_ready[1], p_phase[1]);
+          p_phase[1] ^= 1;
+          tc_fence_after();
+          RFA_STAMP(true, xi, 4);
+          if (leader) issue_pv(1, cur.v_slot, o_started[1]);
+          o_started[1] = true;
+        }
+        if (leader) {
+          umma_commit(&bars->kv_empty[cur.v_slot]);
+          if (nx.valid) {
+            if (nx.a1) issue_qk(1, nx.k_slot);
+            umma_commit(&bars->kv_empty[nx.k_slot]);
+          }
+        }
+        RFA_STAMP(true, xi, 5);
+        cur = nx;
+        ++xi;
+        __syncwarp();
       }
       if (leader) {
         umma_commit(&bars->o_done[0]);

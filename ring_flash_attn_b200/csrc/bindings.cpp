@@ -122,19 +122,7 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
   p.n_items = static_cast<int>(items.size(0));
   p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
-  // opt-in forward variant with 64-key softmax steps (RFA_B200_FWD_H64=1), bf16 / fp16 without windows only
-  static const bool h64 = [] {
-    const char* e = std::getenv("RFA_B200_FWD_H64");
-    return e != nullptr && std::atoi(e) != 0;
-  }();
-  auto* launch_fwd = (h64 && !fp8 && seg_lo == nullptr) ? &rfa::attn_fwd_h64_launch : &rfa::attn_fwd_launch;
-  {
-    static const int fwd_flags = [] {
-      const char* e = std::getenv("RFA_B200_FWD_FLAGS");
-      return e ? std::atoi(e) : 0;
-    }();
-    p.flags = fwd_flags;
-  }
+  auto* launch_fwd = &rfa::attn_fwd_launch;
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
@@ -209,8 +197,9 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
               dq_accum.stride(2) == 1);
   if (fc == nullptr) {
     TORCH_CHECK(dk.has_value() && dv.has_value());
-    TORCH_CHECK(dk->scalar_type() == at::kFloat && dk->is_contiguous() && dv->scalar_type() == at::kFloat &&
-                dv->is_contiguous());
+    TORCH_CHECK(dk->is_contiguous() && dv->is_contiguous() && dk->scalar_type() == dv->scalar_type());
+    TORCH_CHECK(dk->scalar_type() == at::kFloat || dk->scalar_type() == q.scalar_type(),
+                "dk / dv must be fp32 (accumulating transports) or the model dtype");
   }
   TORCH_CHECK(lse.scalar_type() == at::kFloat && delta.scalar_type() == at::kFloat);
   rfa::BwdParams p{};
@@ -218,8 +207,9 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
   p.qsegs = reinterpret_cast<const rfa::BwdQSegment*>(qsegs.data_ptr());
   p.lse = lse.data_ptr<float>();
   p.delta = delta.data_ptr<float>();
-  p.dk = dk.has_value() ? dk->data_ptr<float>() : nullptr;
-  p.dv = dv.has_value() ? dv->data_ptr<float>() : nullptr;
+  p.dk = dk.has_value() ? dk->data_ptr() : nullptr;
+  p.dv = dv.has_value() ? dv->data_ptr() : nullptr;
+  p.dkv_fp32 = (dk.has_value() && dk->scalar_type() == at::kFloat) ? 1 : 0;
   p.lse_S = static_cast<int>(lse_S);
   p.hq = static_cast<int>(q.size(1));
   p.hkv = static_cast<int>(k.size(1));
@@ -229,18 +219,6 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
                  dq_accum.stride(1)};
   p.n_items = static_cast<int>(items.size(0));
   p.window = window ? 1 : 0;
-  {
-    static const int dq_direct = [] {
-      const char* e = std::getenv("RFA_B200_BWD_V2");  // bit 0: direct dQ reduction, bit 1: dS^T in TMEM
-      return e ? std::atoi(e) : 0;
-    }();
-    p.dq_direct = dq_direct;
-    p.dq = dq_accum.data_ptr<float>();
-    p.dq_row_stride = dq_accum.stride(0);
-    p.dq_head_stride = dq_accum.stride(1);
-    p.dq_rows = static_cast<int>(dq_accum.size(0));
-  }
-  if (const char* e = std::getenv("RFA_B200_DEBUG")) p.debug = std::atoi(e);
   p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
@@ -251,18 +229,11 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
     p.dkv.sent_count = cnt + 32;
     p.dkv.epoch = static_cast<uint32_t>(fc->epoch);
     p.dkv.wait_epoch = static_cast<uint32_t>(fc->dkv_wait_epoch);
-    {
-      static const int bulk = [] {
-        const char* e = std::getenv("RFA_B200_DKV_BULK");
-        return e ? std::atoi(e) : 0;
-      }();
-      p.dkv.bulk = bulk;
-    }
     p.dkv.world = static_cast<int>(fc->world);
     p.dkv.my_rank = static_cast<int>(fc->my_rank);
     for (int r = 0; r < fc->world; ++r) {
-      p.dkv.dk_ptrs[r] = reinterpret_cast<float*>(fc->dk_ptrs[r]);
-      p.dkv.dv_ptrs[r] = reinterpret_cast<float*>(fc->dv_ptrs[r]);
+      p.dkv.dk_ptrs[r] = reinterpret_cast<void*>(fc->dk_ptrs[r]);
+      p.dkv.dv_ptrs[r] = reinterpret_cast<void*>(fc->dv_ptrs[r]);
       p.dkv.peer_pads[r] = reinterpret_cast<uint32_t*>(fc->pad_ptrs[r]);
       p.dkv.sent_target[r] = static_cast<uint32_t>(fc->dkv_targets[r]);
     }
@@ -306,12 +277,12 @@ void attn_bwd_fused_window(const at::Tensor& q, const at::Tensor& dout, const at
 void reduce_dkv(const at::Tensor& inbox, int64_t slot_stride, int64_t kv_stride, at::Tensor& dk, at::Tensor& dv,
                 const at::Tensor& tasks, const FusedCtx& fc, int64_t ticket_target) {
   const c10::cuda::CUDAGuard guard(inbox.device());
-  TORCH_CHECK(inbox.scalar_type() == at::kFloat && dk.is_contiguous() && dv.is_contiguous());
+  TORCH_CHECK(inbox.scalar_type() == dk.scalar_type() && dk.is_contiguous() && dv.is_contiguous());
   TORCH_CHECK(tasks.scalar_type() == at::kInt && tasks.is_contiguous() && tasks.size(1) == 4);
   rfa::ReduceParams p{};
   p.tasks = reinterpret_cast<const rfa::ReduceTask*>(tasks.data_ptr());
   p.n_tasks = static_cast<int>(tasks.size(0));
-  p.inbox = inbox.data_ptr<float>();
+  p.inbox = inbox.data_ptr();
   p.slot_stride = slot_stride;
   p.kv_stride = kv_stride;
   p.dk = dk.data_ptr();
@@ -325,6 +296,15 @@ void reduce_dkv(const at::Tensor& inbox, int64_t slot_stride, int64_t kv_stride,
   p.my_rank = static_cast<int>(fc.my_rank);
   for (int r = 0; r < fc.world; ++r) p.peer_pads[r] = reinterpret_cast<uint32_t*>(fc.pad_ptrs[r]);
   check(rfa::reduce_dkv_launch(dtype_code(dk), p, at::cuda::getCurrentCUDAStream()));
+}
+
+// dq = cast(acc); acc = 0  (csrc/comm_sm100.cu: dq_finalize_kernel)
+void dq_finalize(at::Tensor& acc, at::Tensor& out) {
+  const c10::cuda::CUDAGuard guard(acc.device());
+  TORCH_CHECK(acc.scalar_type() == at::kFloat && acc.is_contiguous() && out.is_contiguous() &&
+              acc.numel() == out.numel());
+  check(rfa::dq_finalize_launch(dtype_code(out), acc.data_ptr<float>(), out.data_ptr(), acc.numel(),
+                                at::cuda::getCurrentCUDAStream()));
 }
 
 // kind::f8f6f4 descriptor probe (csrc/probe_fp8_sm100.cu): a, b are (128, 128) float8_e4m3fn tensors;
@@ -435,6 +415,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_bwd_fused_window", &attn_bwd_fused_window);
   m.def("attn_bwd_fused", &attn_bwd_fused);
   m.def("reduce_dkv", &reduce_dkv);
+  m.def("dq_finalize", &dq_finalize);
   m.def("attn_bwd_delta", &attn_bwd_delta);
   m.def("attn_bwd", &attn_bwd);
   m.def("probe", &probe);

@@ -1,7 +1,7 @@
 // Owner-side reduction of the backward "inbox".
 //
-// During the fused backward every rank stores its fp32 dK/dV partials for a shard directly into the shard
-// owner's inbox slot over NVLink (attn_bwd_sm100.cu epilogue).  This kernel runs on the owner afterwards:
+// During the fused backward every rank stores its dK/dV partials for a shard (rounded once to the model dtype)
+// directly into the shard owner's inbox slot over NVLink (attn_bwd_sm100.cu epilogue).  This kernel runs on the owner afterwards:
 // it waits until every contributing rank has raised its "gradients landed" epoch, sums the slots that hold a
 // partial for each row range in a fixed order (so the result is deterministic), writes dK/dV in the model
 // dtype and finally tells every peer that the inbox may be reused.  It replaces the reference's W-hop fp32
@@ -27,7 +27,30 @@ __device__ __forceinline__ uint2 pack4<__half>(const float4& a) {
   return make_uint2(Pack2<__half>::pack(a.x, a.y), Pack2<__half>::pack(a.z, a.w));
 }
 
-// grid: (blocks_per_task, n_tasks)
+template <typename T>
+__device__ __forceinline__ float4 unpack4(const uint2& a);
+template <>
+__device__ __forceinline__ float4 unpack4<__nv_bfloat16>(const uint2& a) {
+  // bf16 -> fp32 is a 16-bit shift
+  return make_float4(__uint_as_float(a.x << 16), __uint_as_float(a.x & 0xffff0000u), __uint_as_float(a.y << 16),
+                     __uint_as_float(a.y & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float4 unpack4<__half>(const uint2& a) {
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ uint2 ldcv_u2(const uint2* p) {
+  uint2 r;
+  // written by a peer over NVLink: always read from L2, never from a stale L1 line
+  asm volatile("ld.global.cv.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// grid: (blocks_per_task, n_tasks).  The partials arrive in the model dtype (the backward epilogue rounds each
+// rank's fp32 tile once - what flash-attn does for every block in the reference, ring_flash_attn.py:131-141) and
+// are summed here in fp32 in fixed rank order.
 template <typename T>
 __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__ ReduceParams p) {
   const ReduceTask t = p.tasks[blockIdx.y];
@@ -45,7 +68,7 @@ __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   constexpr int U = 4;
   for (int which = 0; which < 2; ++which) {
-    const float4* in = reinterpret_cast<const float4*>(p.inbox + which * p.kv_stride) + off4;
+    const uint2* in = reinterpret_cast<const uint2*>(static_cast<const T*>(p.inbox) + which * p.kv_stride) + off4;
     uint2* out = reinterpret_cast<uint2*>(which == 0 ? p.dk : p.dv) + off4;
     for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
       float4 acc[U];
@@ -53,21 +76,21 @@ __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__
       for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < p.world; ++r) {
         if (!((t.src_mask >> r) & 1u)) continue;
-        float4 v[U];
+        uint2 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * stride;
-          // written by a peer over NVLink: always read from L2, never from a stale L1 line
-          if (i < n4) v[u] = __ldcv(in + r * slot4 + i);
+          if (i < n4) v[u] = ldcv_u2(in + r * slot4 + i);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * stride;
           if (i < n4) {
-            acc[u].x += v[u].x;
-            acc[u].y += v[u].y;
-            acc[u].z += v[u].z;
-            acc[u].w += v[u].w;
+            const float4 f = unpack4<T>(v[u]);
+            acc[u].x += f.x;
+            acc[u].y += f.y;
+            acc[u].z += f.z;
+            acc[u].w += f.w;
           }
         }
       }
@@ -89,6 +112,21 @@ __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__
   }
 }
 
+// dQ leaves the backward kernel as an fp32 accumulator (key-tile CTAs add their partial tiles with TMA
+// reduce-add).  This kernel turns it into the model dtype AND zeroes the accumulator again, so the workspace is
+// ready for the next backward: one pass of our own instead of a memset before and a cast after every call.
+template <typename T>
+__global__ void __launch_bounds__(256) dq_finalize_kernel(float4* __restrict__ acc, uint2* __restrict__ out,
+                                                          long long n4) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldcs(acc + i);
+    out[i] = pack4<T>(v);
+    acc[i] = zero;
+  }
+}
+
 }  // namespace comm
 
 const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream) {
@@ -98,6 +136,23 @@ const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t str
     comm::reduce_dkv_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
   } else {
     comm::reduce_dkv_kernel<__half><<<grid, 256, 0, stream>>>(p);
+  }
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+const char* dq_finalize_launch(int dtype, float* acc, void* out, long long numel, cudaStream_t stream) {
+  if (numel <= 0) return nullptr;
+  if (numel % 4) return "dq_finalize: element count must be a multiple of 4";
+  const long long n4 = numel / 4;
+  const long long want = (n4 + 255) / 256;
+  const int blocks = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  if (dtype == kDtypeBF16) {
+    comm::dq_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(acc),
+                                                                        static_cast<uint2*>(out), n4);
+  } else {
+    comm::dq_finalize_kernel<__half><<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(acc),
+                                                                 static_cast<uint2*>(out), n4);
   }
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

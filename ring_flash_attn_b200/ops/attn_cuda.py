@@ -34,7 +34,7 @@ def _diag(d: Optional[int]) -> int:
     return DIAG_FULL if d is None else int(d)
 
 
-# ---- experimental fp8 forward (RFA_B200_FP8_KERNEL=1) --------------------------------------------------
+# ---- fp8 forward (e4m3 q / k / v with per-tensor or per-head descales; RFA_B200_FP8_KERNEL=0 disables) ----
 # The per-head descales of the running call; set by parallel/api.py around the engine call so that the
 # executors (which only know q / k / v) can hand them to the launch.
 _FP8_STATE = threading.local()
@@ -72,12 +72,12 @@ def has_window(segs: Sequence[Segment]) -> bool:
 
 
 def window_kernels_enabled() -> bool:
-    """Sliding-window plans run on the kernels only when asked for (``RFA_B200_WINDOW_KERNEL=1``): the kWindow
-    kernel variants were written after the last hardware session of round 1 and are validated in round 2;
-    until then windowed plans use the dense torch blocks (``parallel/engine.py``)."""
+    """Sliding-window plans run on the kWindow kernel variants (validated on B200 in round 2:
+    profiles/r2/trip_single_variants.log, trip_multi2_bulk_configs.log).  ``RFA_B200_WINDOW_KERNEL=0`` forces the
+    dense torch blocks (``parallel/engine.py``) for debugging."""
     import os
 
-    return os.environ.get("RFA_B200_WINDOW_KERNEL", "0") == "1"
+    return os.environ.get("RFA_B200_WINDOW_KERNEL", "1") != "0"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -237,6 +237,11 @@ def bwd_tables_host(plan: CPPlan, segs: Sequence[Segment], row_offset: Dict[int,
     return [it for _, it in items], qsegs
 
 
+def bwd_covers_all_rows(items: List[List[int]], kv_rows: int) -> bool:
+    """True when the (exclusive) key tiles of a backward table write every one of ``kv_rows`` dK/dV rows."""
+    return sum(it[1] for it in items) == kv_rows
+
+
 def bwd_tables_fused(plan: CPPlan, row_offset: Dict[int, int], device, flag_of_src: Dict[int, int]):
     """Backward tables for the fused multi-GPU launch: every key tile carries its owner rank and its row
     inside the owner's shard; tiles that no local query reaches are still emitted (they store zeros into
@@ -279,6 +284,46 @@ def bwd_tables_fused(plan: CPPlan, row_offset: Dict[int, int], device, flag_of_s
     return c[key]
 
 
+class _DqWorkspace:
+    """fp32 dQ accumulators, one per (device, stream, element count), kept ZEROED between calls: the backward
+    kernel adds its partial tiles into it and ``dq_finalize`` (csrc/comm_sm100.cu) writes the model-dtype result and
+    zeroes the accumulator again in the same pass.  Replaces a ``torch.zeros`` before and a ``.to(dtype)`` after
+    every backward (the reference's fp32 dq bookkeeping: /root/reference/ring_flash_attn/ring_flash_attn.py:134-154)."""
+
+    def __init__(self):
+        self._bufs: Dict[tuple, list] = {}
+
+    @staticmethod
+    def _key(q: torch.Tensor) -> tuple:
+        stream = torch.cuda.current_stream(q.device).cuda_stream if q.is_cuda else 0
+        return (str(q.device), stream, q.numel())
+
+    def acquire(self, q: torch.Tensor) -> torch.Tensor:
+        key = self._key(q)
+        ent = self._bufs.get(key)
+        if ent is None:
+            if len(self._bufs) >= 8:  # a handful of live shapes; drop the oldest
+                self._bufs.pop(next(iter(self._bufs)))
+            ent = [torch.zeros(q.numel(), dtype=torch.float32, device=q.device), False]
+            self._bufs[key] = ent
+        elif ent[1]:  # a previous backward died between launch and finalize: do not trust the contents
+            ent[0].zero_()
+        ent[1] = True
+        return ent[0].view(q.shape)
+
+    def finalize(self, acc: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+        cuda_ext.load().dq_finalize(acc.view(-1), out.view(-1))
+        cuda_ext.note_launch()
+        ent = self._bufs.get(self._key(q))
+        if ent is not None and ent[0].data_ptr() == acc.data_ptr():
+            ent[1] = False
+        return out
+
+
+dq_workspace = _DqWorkspace()
+
+
 def _to_dev(rows: List[List[int]], width: int, device) -> torch.Tensor:
     if not rows:
         return torch.zeros((0, width), dtype=torch.int32, device=device)
@@ -308,7 +353,13 @@ def bwd_tables(plan, segs, row_offset, device, key, flag_of_src=None):
     if k not in c:
         items, qsegs = bwd_tables_host(plan, segs, row_offset, flag_of_src)
         c[k] = (_to_dev(items, 8, device), _to_dev(qsegs, 4, device))
+        c[k + ("covered",)] = bwd_covers_all_rows(items, plan.kv_rows)
     return c[k]
+
+
+def bwd_tables_cover(plan, device, key) -> bool:
+    """Whether the cached backward table ``key`` writes every local dK/dV row (else the outputs start as zeros)."""
+    return bool(_cache(plan).get(("bwd", key, device.index, "covered"), False))
 
 
 # ----------------------------------------------------------------------------------------------

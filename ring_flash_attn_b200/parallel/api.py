@@ -126,7 +126,7 @@ def _fp8_kernel_scales(q, k, v, dq, dk, dv, window_size):
     """Descales for the experimental fp8 forward kernel, or None when the call does not qualify: opt-in
     (``RFA_B200_FP8_KERNEL=1``), e4m3 q/k/v with head_dim 128 on a Blackwell GPU, per-tensor or per-head
     descales, no sliding window.  Finer block scales take the dequantise-to-bf16 path."""
-    if os.environ.get("RFA_B200_FP8_KERNEL", "0") != "1":
+    if os.environ.get("RFA_B200_FP8_KERNEL", "2") == "0":
         return None
     if not (q.dtype == k.dtype == v.dtype == torch.float8_e4m3fn) or q.shape[-1] != 128:
         return None

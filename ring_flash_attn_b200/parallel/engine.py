@@ -55,8 +55,8 @@ def plan_has_window(plan: CPPlan) -> bool:
 
 
 def _kernels_take(plan: CPPlan) -> bool:
-    """Windowed plans run on the kWindow kernel variants only with RFA_B200_WINDOW_KERNEL=1 (see
-    ``ops/attn_cuda.py:window_kernels_enabled``); otherwise on the dense torch blocks, on any device."""
+    """Windowed plans run on the kWindow kernel variants unless RFA_B200_WINDOW_KERNEL=0 (see
+    ``ops/attn_cuda.py:window_kernels_enabled``); then on the dense torch blocks, on any device."""
     if not plan_has_window(plan):
         return True
     from ..ops import attn_cuda
@@ -296,8 +296,8 @@ def allgather_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, head
 def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
     if not _use_cuda_kernels(q, k):
         return False
-    if q.element_size() == 1 and os.environ.get("RFA_B200_FP8_KERNEL", "0") != "2":
-        return False  # fp8 forward inside the fused launch: second opt-in level (=2), validated after level 1
+    if q.element_size() == 1 and os.environ.get("RFA_B200_FP8_KERNEL", "2") == "1":
+        return False  # =1: fp8 kernel on the per-source transports only (e4m3 over NCCL), not inside the fused launch
     if plan is not None and (not getattr(plan, "fused_ok", True) or not _kernels_take(plan)):
         return False
     from . import fused

@@ -44,15 +44,18 @@ def _forward_local(plan: CPPlan, q, k, v, scale):
 
 def _backward_local(plan: CPPlan, dout, q, k, v, out, lse, scale):
     delta = attn_cuda.compute_delta(out, dout)
-    dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
-    dk = torch.zeros(k.shape, dtype=torch.float32, device=q.device)
-    dv = torch.zeros(v.shape, dtype=torch.float32, device=q.device)
+    dq = attn_cuda.dq_workspace.acquire(q)  # zeroed fp32 accumulator, re-zeroed by dq_finalize
     if attn_cuda.has_window(plan.segments):
+        # windowed tables may leave key tiles without any query: start from zeros (model dtype)
+        dk, dv = torch.zeros_like(k), torch.zeros_like(v)
         attn_cuda.segments_backward(plan, plan.segments, dout, q, k, v, lse, delta, scale, dq, dk, dv)
     else:
         items, qsegs = attn_cuda.bwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
+        # every key tile has exactly one writer and the epilogue stores the model dtype: no memset, no cast
+        alloc = torch.empty_like if attn_cuda.bwd_tables_cover(plan, q.device, ("local",)) else torch.zeros_like
+        dk, dv = alloc(k), alloc(v)
         attn_cuda.backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq, dk, dv)
-    return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
+    return attn_cuda.dq_workspace.finalize(dq, q), dk, dv
 
 
 def forward(plan: CPPlan, q, k, v, scale, group):

@@ -6,8 +6,8 @@ rank of the group maps (``csrc/peer_mem.cpp``):
 * the *signal pad*   - uint32 epochs written by peers (layout in ``csrc/attn_common.h``: kPad*),
 * the *K/V staging*  - ``[parity][K|V][slot = source rank][rows][hkv][128]``: the rows of every other rank's
                        shard that this rank's plan needs, stored there by the *source's* attention kernel,
-* the *dK/dV inbox*  - ``[slot = source rank][dK|dV][rows][hkv][128]`` fp32: partial gradients for this
-                       rank's shard, stored there by the peers' backward kernels.
+* the *dK/dV inbox*  - ``[slot = source rank][dK|dV][rows][hkv][128]`` in the model dtype: partial gradients for
+                       this rank's shard, stored there by the peers' backward kernels (summed in fp32 by the owner).
 
 A forward is ONE launch of ``attn_fwd_kernel``: its first CTAs push this rank's K/V rows to the peers that
 need them (ring order; TMA bulk copies HBM -> shared memory -> peer HBM), the rest run the math and only wait on
@@ -103,9 +103,10 @@ class PeerContext:
         self.stage = PeerBuffer(2 * self.stage_half, self.device, self.group)
         self._quiesce()
 
-    def ensure_inbox(self, rows: int, hkv: int) -> None:
-        need = self.world * 2 * rows * hkv * 128 * 4
-        self.inbox_kv_stride = rows * hkv * 128  # floats
+    def ensure_inbox(self, rows: int, hkv: int, dtype) -> None:
+        esize = torch.empty((), dtype=dtype).element_size()
+        need = self.world * 2 * rows * hkv * 128 * esize
+        self.inbox_kv_stride = rows * hkv * 128  # elements
         self.inbox_slot_stride = 2 * self.inbox_kv_stride
         if self.inbox is not None and need <= self.inbox.nbytes:
             return
@@ -319,7 +320,7 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     k, v = _kv_ok(k), _kv_ok(v)
     rows, hkv = plan.kv_rows, k.shape[1]
     ctx.ensure_stage(rows, hkv, k.dtype)
-    ctx.ensure_inbox(rows, hkv)
+    ctx.ensure_inbox(rows, hkv, k.dtype)
     offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
     flags = {s: s for s in range(plan.world) if s != plan.rank}
     window = attn_cuda.has_window(plan.segments)
@@ -334,11 +335,11 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     else:
         items, qsegs, per_owner = attn_cuda.bwd_tables_fused(plan, offsets, q.device, flags)
     delta = attn_cuda.compute_delta(out, dout)
-    dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    dq = attn_cuda.dq_workspace.acquire(q)  # zeroed fp32 accumulator, re-zeroed by dq_finalize
     fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hkv)
-    me = plan.rank
-    fc.dk_ptrs = [p + me * ctx.inbox_slot_stride * 4 for p in ctx.inbox.ptrs]
-    fc.dv_ptrs = [p + (me * ctx.inbox_slot_stride + ctx.inbox_kv_stride) * 4 for p in ctx.inbox.ptrs]
+    me, esize = plan.rank, k.element_size()
+    fc.dk_ptrs = [p + me * ctx.inbox_slot_stride * esize for p in ctx.inbox.ptrs]
+    fc.dv_ptrs = [p + (me * ctx.inbox_slot_stride + ctx.inbox_kv_stride) * esize for p in ctx.inbox.ptrs]
     for o in range(plan.world):
         ctx.dkv_cum[o] = (ctx.dkv_cum[o] + per_owner[o] * hkv) & MASK32
     fc.dkv_targets = list(ctx.dkv_cum)
@@ -351,9 +352,9 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     tasks = reduce_tasks(plan, ctx, q.device)
     dk = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
     dv = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
-    inbox = ctx.inbox.tensor(0, (ctx.world * ctx.inbox_slot_stride,), torch.float32)
+    inbox = ctx.inbox.tensor(0, (ctx.world * ctx.inbox_slot_stride,), k.dtype)
     ctx.ticket_cum = (ctx.ticket_cum + 128 * int(tasks.shape[0])) & MASK32  # kReduceBlocksPerTask
     C.reduce_dkv(inbox, ctx.inbox_slot_stride, ctx.inbox_kv_stride, dk, dv, tasks, fc, ctx.ticket_cum)
     cuda_ext.note_launch()
     ctx.last_bwd_epoch = ctx.epoch
-    return dq.to(q.dtype), dk, dv
+    return attn_cuda.dq_workspace.finalize(dq, q), dk, dv

@@ -103,6 +103,11 @@ class FakeExt:
             dk[kv_row0:kv_row0 + kv_rows] = dk_t.view(kv_rows, hkv, rep, d).sum(2)  # written, not accumulated
             dv[kv_row0:kv_row0 + kv_rows] = dv_t.view(kv_rows, hkv, rep, d).sum(2)
 
+    def dq_finalize(self, acc, out):
+        self.calls.append("dq_finalize")
+        out.copy_(acc.to(out.dtype))
+        acc.zero_()
+
     def attn_bwd(self, q, dout, k, v, dq, items, qsegs, lse, delta, dk, dv, lse_S, scale):
         self.calls.append("attn_bwd")
         self._bwd(q, dout, k, v, dq, items, qsegs, lse, delta, dk, dv, scale, False)

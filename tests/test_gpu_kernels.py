@@ -222,12 +222,6 @@ def test_world1_zigzag_llama3():
     assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
 
 
-_EXPERIMENTAL = pytest.mark.skipif(
-    __import__("os").environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
-    reason="kernel variants written after the last hardware session; enable with RFA_B200_TEST_EXPERIMENTAL=1")
-
-
-@_EXPERIMENTAL
 @pytest.mark.parametrize("fn_name,causal,window", [
     ("zigzag_ring_flash_attn_kvpacked_func", True, (100, 0)),
     ("ring_flash_attn_kvpacked_func", True, (700, 0)),
@@ -236,10 +230,10 @@ _EXPERIMENTAL = pytest.mark.skipif(
     ("ring_flash_attn_kvpacked_func", False, (-1, 200)),
 ])
 def test_sliding_window_kernels(monkeypatch, fn_name, causal, window):
-    """kWindow variants of both kernels (RFA_B200_WINDOW_KERNEL=1) against the windowed oracle."""
+    """kWindow variants of both kernels (the default for windowed plans) against the windowed oracle."""
     from ring_flash_attn_b200.ops import cuda_ext
 
-    monkeypatch.setenv("RFA_B200_WINDOW_KERNEL", "1")
+    monkeypatch.delenv("RFA_B200_WINDOW_KERNEL", raising=False)
     torch.manual_seed(0)
     q = torch.randn(2, 1000, 8, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
     kv = torch.randn(2, 1000, 2, 2, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
@@ -257,7 +251,6 @@ def test_sliding_window_kernels(monkeypatch, fn_name, causal, window):
     assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
 
 
-@_EXPERIMENTAL
 def test_fp8_descriptor_probe():
     """kind::f8f6f4 operand forms of the fp8 forward (benchmark/probe_fp8.py sweeps alternatives on a mismatch)."""
     C = _ext()
@@ -270,15 +263,14 @@ def test_fp8_descriptor_probe():
         assert (out - ref).abs().max().item() < 1e-3 * max(ref.abs().max().item(), 1.0), (a_kind, b_kind)
 
 
-@_EXPERIMENTAL
 @pytest.mark.parametrize("per_head", [False, True])
 def test_fp8_forward_kernel(monkeypatch, per_head):
-    """RFA_B200_FP8_KERNEL=1: e4m3 q/k/v go straight into the forward kernel (kind::f8f6f4 for both GEMMs, P as
+    """Default for per-tensor / per-head descales: e4m3 q/k/v go straight into the forward kernel (kind::f8f6f4 for both GEMMs, P as
     e4m3 in tensor memory); compared with the oracle on the dequantised tensors at fp8 tolerance."""
     from ring_flash_attn_b200.ops import cuda_ext
     from ring_flash_attn_b200.utils import fp8
 
-    monkeypatch.setenv("RFA_B200_FP8_KERNEL", "1")
+    monkeypatch.delenv("RFA_B200_FP8_KERNEL", raising=False)
     torch.manual_seed(0)
     q = torch.randn(1, 900, 8, 128, device="cuda") * 1.5
     kv = torch.randn(1, 900, 2, 2, 128, device="cuda") * 1.5
@@ -300,7 +292,6 @@ def test_fp8_forward_kernel(monkeypatch, per_head):
     assert err < 6e-2 * ref.abs().max().item() + 2e-2, err
 
 
-@_EXPERIMENTAL
 def test_single_token_documents():
     """Degenerate packing (documents of one token, chunks of one row): covered by the CPU table tests, run on hardware
     with the other round-2 checks."""

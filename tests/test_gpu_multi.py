@@ -193,7 +193,7 @@ def test_zigzag_llama3_2gpu(p2p):
 
 
 def _window_fused_case(rank, world, p2p):
-    os.environ["RFA_B200_WINDOW_KERNEL"] = "1"
+    os.environ.pop("RFA_B200_WINDOW_KERNEL", None)  # the kWindow kernel variants are the default
     os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"
     dev = torch.device("cuda", rank)
     torch.manual_seed(0)
@@ -221,8 +221,6 @@ def _window_fused_case(rank, world, p2p):
         assert (lkv.grad.float() - gkv).abs().max().item() < 5e-2 * gkv.abs().max().item() + 2e-2
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="kWindow kernel variants are validated in round 2 (RFA_B200_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("p2p", [True, False])
 def test_sliding_window_kernels_2gpu(p2p):
     if _ngpu() < 2:
@@ -251,8 +249,6 @@ def _subgroup_fused_case(rank, world):
         _close(out, layouts.shard_zigzag(ref, grank, gworld), "out")
 
 
-@pytest.mark.skipif(os.environ.get("RFA_B200_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="not yet run on hardware (RFA_B200_TEST_EXPERIMENTAL=1)")
 def test_fused_subgroups_4gpu():
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs")
