@@ -142,7 +142,7 @@ def main():
 
     fwd = args.forward_only
     d = 16 if args.tiny else 128
-    from ring_flash_attn_b200.parallel import api as _api
+    from ring_flash_attn_b200.parallel import ops as _ops
     from ring_flash_attn_b200.parallel.symm import _ranges
 
     def link_bytes(plan, hkv, batch=1):
@@ -162,7 +162,7 @@ def main():
             dout = rnd(1, L, H, d)
             fn = mod.zigzag_ring_flash_attn_qkvpacked_func
             ms, med = measure(run_fb(lambda: fn(qkv, causal=True), [qkv], dout))
-            rx = link_bytes(_api._batch_plan("zigzag", rank, world, 1, L, True), H)
+            rx = link_bytes(_ops.batch_plan("zigzag", rank, world, 1, L, True), H)
             report(name, "zigzag_ring_flash_attn_qkvpacked_func", ms, med, causal_flops([S], H, d, fwd) / world, rx,
                    {"seq_len": S, "nheads": H})
         elif name == "varlen":
@@ -177,7 +177,7 @@ def main():
             dout = rnd(L, H, d)
             fn = mod.zigzag_ring_flash_attn_varlen_qkvpacked_func
             ms, med = measure(run_fb(lambda: fn(qkv, local_cu, max_s, causal=True), [qkv], dout))
-            rx = link_bytes(_api._varlen_plan("zigzag", rank, world, tuple(c // world for c in cu), True), H)
+            rx = link_bytes(_ops.varlen_plan("zigzag", rank, world, tuple(c // world for c in cu), True), H)
             report(name, "zigzag_ring_flash_attn_varlen_qkvpacked_func", ms, med,
                    causal_flops(lens, H, d, fwd) / world, rx, {"total_seq": S, "docs": lens, "nheads": H})
         elif name == "llama3":
@@ -195,7 +195,7 @@ def main():
             ms, med = measure(run_fb(lambda: fn(q, k, v, cq, ck, mq, mk, heads_k_stride=1, local_k_slice=ks,
                                                 causal=True), [q, k, v], dout))
             # this rank's share of the causal work: its queries against the keys of their documents up to them
-            rx = link_bytes(_api._llama3_plan(rank, world, L, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start),
+            rx = link_bytes(_ops.llama3_plan(rank, world, L, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start),
                                               True), HK)
             lo, hi = rank * L, (rank + 1) * L
             pairs, start = 0.0, 0
@@ -236,7 +236,7 @@ def main():
                 fn = mod.stripe_flash_attn_qkvpacked_func
                 step = run_fb(lambda: fn(deq, causal=True), [deq], dout)
             ms, med = measure(step)
-            rx = link_bytes(_api._batch_plan("stripe", rank, world, B, L, True), H)
+            rx = link_bytes(_ops.batch_plan("stripe", rank, world, B, L, True), H)
             report(name, "stripe_flash_attn_qkvpacked_func", ms, med, B * causal_flops([S], H, d, fwd) / world, rx,
                    {"batch": B, "seq_len": S, "nheads": H, "inputs": "e4m3 + per-128-token scales" if fwd and
                     args.impl == "ours" else "bf16 (dequantised)"})

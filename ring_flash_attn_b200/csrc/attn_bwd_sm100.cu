@@ -171,7 +171,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     reg_dealloc<72>();  // 128*72 + 384*144 = 512*126 <= 512*128
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
-      if (lane == 0) {
+      // (a tile no local query reaches only sends zero rows: nothing is loaded, and in particular no TMA write can
+      // land in the K | V area after the epilogue has started to stage those rows there)
+      if (lane == 0 && total_tiles > 0) {
         const bool staged = it.flag >= 0 && p.ready_flags != nullptr;
         if (staged) {
           wait_epoch(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready", p.sig.my_rank, it.flag);
@@ -660,6 +662,7 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
                             const TensorView& dq_accum, const BwdParams& p, cudaStream_t stream) {
   const int n_blocks = p.push.n_ctas + p.n_items * p.hkv;
   if (n_blocks <= 0) return nullptr;
+  if (p.sig.world > 0) set_peer_timeout_from_env();
   CUtensorMap tq, tdo, tk, tv, tks, tvs, tdq;
   if (const char* e = make_tensor_map(&tq, q, 2, bwd::kTileQ, bwd::kD)) return e;
   if (const char* e = make_tensor_map(&tdo, dout, 2, bwd::kTileQ, bwd::kD)) return e;

@@ -55,8 +55,19 @@ struct alignas(16) PushTask {
   int pad;
 };
 
+// Plans that cannot derive their peers' plans locally (llama3: a rank only sees its own cu_seqlens slice) learn
+// what every peer needs at run time: each rank's (source -> up to kNeedRanges row ranges) table is all-gathered
+// on the device right before the launch and the push / reduce roles derive their work from it.
+constexpr int kNeedRanges = 4;
+
 struct PushParams {
-  const PushTask* tasks;
+  const PushTask* tasks;  // static mode: host-built table (plans that know their peers' plans)
+  const int* dyn_needs;   // dynamic mode (tasks == nullptr): [dst][src][kNeedRanges][2] = (lo, hi) rows of src's shard
+  int dyn_chunk_rows;     // rows per dynamic task
+  int dyn_chunks;         // dynamic tasks per (destination, K|V, range)
+  int world;
+  long long region_bytes;  // bytes of the K half of one staging parity (V follows)
+  int rows_cap;            // rows per source slot in the staging buffer
   int n_tasks;
   int n_ctas;     // blocks [0, n_ctas) of the grid are push CTAs
   int row_bytes;  // bytes per staged row (kv heads * 128 * 2)
@@ -104,6 +115,7 @@ struct alignas(16) ReduceTask {
 };
 struct ReduceParams {
   const ReduceTask* tasks;
+  const int* dyn_needs;  // dynamic mode: the same all-gathered table (rows of MY shard that rank s returns = what it read)
   int n_tasks;
   const void* inbox;      // [world][2][rows_cap * hkv * 128], model dtype
   long long slot_stride;  // elements between slots
@@ -129,6 +141,7 @@ struct FwdParams {
   const int* seg_lo;  // sliding window only (else nullptr): per segment, key j visible to chunk row i iff j >= i + lo
   const float* head_scale_qk;  // fp8 only: q_descale * k_descale per QUERY head (multiplies the softmax scale)
   const float* head_scale_v;   // fp8 only: v_descale per KV head (multiplies the output)
+  int flags;  // tuning switches (RFA_B200_FWD_FLAGS): bit 0 = no turn-taking between the two softmax warpgroups
   void* out;  // (rows, hq, 128) contiguous, input dtype
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;

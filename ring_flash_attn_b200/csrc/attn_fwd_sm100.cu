@@ -410,15 +410,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // and the tensor pipe idles while both run.  Strict alternation keeps one tile's softmax under the other
     // tile's MMAs.  Both groups execute one hand-off per key tile, active or not, so the counts always match.
     int handoffs_left = 0;
-    if (has_t1) {
+    const bool take_turns = has_t1 && !(p.flags & 1);
+    if (take_turns) {
       for (int si = 0; si < it.seg_count; ++si) handoffs_left += seg_geom(p.segs[it.seg_begin + si], it).n_tiles;
       if (t == 1 && handoffs_left > 0) named_bar_arrive(1, 256);  // tile 0 goes first
     }
     auto turn_wait = [&]() {
-      if (has_t1) named_bar_sync(1 + t, 256);
+      if (take_turns) named_bar_sync(1 + t, 256);
     };
     auto turn_pass = [&]() {
-      if (has_t1) {
+      if (take_turns) {
         --handoffs_left;
         if (!(t == 1 && handoffs_left == 0)) named_bar_arrive(1 + (1 - t), 256);  // nobody waits after the last one
       }
@@ -616,6 +617,7 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
                             cudaStream_t stream) {
   const int n_blocks = p.push.n_ctas + p.n_items * p.hq;
   if (n_blocks <= 0) return nullptr;
+  if (p.sig.world > 0) set_peer_timeout_from_env();
   CUtensorMap tq, tk, tv, tks, tvs;
   const int eb = dtype == kDtypeE4M3 ? 1 : 2;
   if (dtype == kDtypeE4M3 && (p.head_scale_qk == nullptr || p.head_scale_v == nullptr || p.seg_lo != nullptr))

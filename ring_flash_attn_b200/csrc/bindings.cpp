@@ -34,7 +34,9 @@ extern at::Tensor g_trace;
 struct FusedCtx {
   at::Tensor k_stage, v_stage;   // (world * rows_cap, hkv, 128) views of this rank's staging buffer (current parity)
   at::Tensor my_pad;             // int32 view of this rank's signal pad
-  at::Tensor push_tasks;         // int64 (n, 4)
+  at::Tensor push_tasks;         // int64 (n, 4); static mode
+  c10::optional<at::Tensor> dyn_needs;  // int32 (world, world, kNeedRanges, 2): dynamic mode (llama3), see attn_common.h
+  int64_t dyn_chunk_rows = 0, dyn_chunks = 0, rows_cap = 0, region_bytes = 0;
   at::Tensor counters;           // int32 (64): [0,16) kv sent, [16] done, [32,48) dkv sent, [48] reduce ticket
   std::vector<int64_t> stage_ptrs, pad_ptrs, sent_targets;
   int64_t n_push_ctas = 0, row_bytes = 0, my_rank = 0, world = 0, epoch = 0, done_target = 0, parity_off = 0;
@@ -48,8 +50,22 @@ void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, co
   TORCH_CHECK(c.push_tasks.scalar_type() == at::kLong && c.push_tasks.is_contiguous());
   TORCH_CHECK(k.stride(1) == 128 && v.stride(1) == 128, "K/V heads must be contiguous inside a row for the push path");
   uint32_t* cnt = reinterpret_cast<uint32_t*>(c.counters.data_ptr());
-  pp.tasks = reinterpret_cast<const rfa::PushTask*>(c.push_tasks.data_ptr());
-  pp.n_tasks = static_cast<int>(c.push_tasks.size(0));
+  pp.world = static_cast<int>(c.world);
+  pp.rows_cap = static_cast<int>(c.rows_cap);
+  pp.region_bytes = c.region_bytes;
+  if (c.dyn_needs.has_value()) {
+    const at::Tensor& nd = *c.dyn_needs;
+    TORCH_CHECK(nd.scalar_type() == at::kInt && nd.is_cuda() && nd.is_contiguous() &&
+                nd.numel() == c.world * c.world * rfa::kNeedRanges * 2, "dyn_needs: int32 (world, world, ranges, 2)");
+    pp.tasks = nullptr;
+    pp.dyn_needs = nd.data_ptr<int>();
+    pp.dyn_chunk_rows = static_cast<int>(c.dyn_chunk_rows);
+    pp.dyn_chunks = static_cast<int>(c.dyn_chunks);
+    pp.n_tasks = static_cast<int>((c.world - 1) * 2 * rfa::kNeedRanges * c.dyn_chunks);
+  } else {
+    pp.tasks = reinterpret_cast<const rfa::PushTask*>(c.push_tasks.data_ptr());
+    pp.n_tasks = static_cast<int>(c.push_tasks.size(0));
+  }
   pp.n_ctas = pp.n_tasks > 0 ? static_cast<int>(c.n_push_ctas) : 0;
   pp.row_bytes = static_cast<int>(c.row_bytes);
   pp.my_rank = static_cast<int>(c.my_rank);
@@ -123,6 +139,13 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   p.n_items = static_cast<int>(items.size(0));
   p.trace = g_trace.defined() ? reinterpret_cast<unsigned long long*>(g_trace.data_ptr()) : nullptr;
   auto* launch_fwd = &rfa::attn_fwd_launch;
+  {
+    static const int fwd_flags = [] {
+      const char* e = std::getenv("RFA_B200_FWD_FLAGS");
+      return e ? std::atoi(e) : 0;
+    }();
+    p.flags = fwd_flags;
+  }
   if (fc != nullptr) {
     p.ready_flags = reinterpret_cast<const uint32_t*>(fc->my_pad.data_ptr()) + rfa::kPadKvReady;
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
@@ -282,6 +305,7 @@ void reduce_dkv(const at::Tensor& inbox, int64_t slot_stride, int64_t kv_stride,
   rfa::ReduceParams p{};
   p.tasks = reinterpret_cast<const rfa::ReduceTask*>(tasks.data_ptr());
   p.n_tasks = static_cast<int>(tasks.size(0));
+  p.dyn_needs = fc.dyn_needs.has_value() ? fc.dyn_needs->data_ptr<int>() : nullptr;
   p.inbox = inbox.data_ptr();
   p.slot_stride = slot_stride;
   p.kv_stride = kv_stride;
@@ -389,6 +413,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("v_stage", &FusedCtx::v_stage)
       .def_readwrite("my_pad", &FusedCtx::my_pad)
       .def_readwrite("push_tasks", &FusedCtx::push_tasks)
+      .def_readwrite("dyn_needs", &FusedCtx::dyn_needs)
+      .def_readwrite("dyn_chunk_rows", &FusedCtx::dyn_chunk_rows)
+      .def_readwrite("dyn_chunks", &FusedCtx::dyn_chunks)
+      .def_readwrite("rows_cap", &FusedCtx::rows_cap)
+      .def_readwrite("region_bytes", &FusedCtx::region_bytes)
       .def_readwrite("counters", &FusedCtx::counters)
       .def_readwrite("stage_ptrs", &FusedCtx::stage_ptrs)
       .def_readwrite("pad_ptrs", &FusedCtx::pad_ptrs)
@@ -404,6 +433,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("dv_ptrs", &FusedCtx::dv_ptrs)
       .def_readwrite("dkv_targets", &FusedCtx::dkv_targets)
       .def_readwrite("dkv_wait_epoch", &FusedCtx::dkv_wait_epoch);
+  m.attr("NEED_RANGES") = rfa::kNeedRanges;
   m.def("set_trace", &set_trace);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_window", &attn_fwd_window);

@@ -14,10 +14,25 @@
 //
 // All cross-GPU flags are monotonically increasing epochs (one per collective call), so nothing is reset.
 #pragma once
+#include <cstdlib>
+
 #include "attn_common.h"
 #include "sm100_ptx.cuh"
 
 namespace rfa {
+
+// Copy RFA_B200_PEER_TIMEOUT_S into this translation unit's g_peer_timeout_ns (once per process and unit).
+inline void set_peer_timeout_from_env() {
+  static const bool done = [] {
+    if (const char* e = std::getenv("RFA_B200_PEER_TIMEOUT_S")) {
+      const double s = std::atof(e);
+      const unsigned long long ns = s <= 0 ? 0ull : static_cast<unsigned long long>(s * 1e9);
+      cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns));
+    }
+    return true;
+  }();
+  (void)done;
+}
 
 // Epochs are compared with wrap-around safe signed distance.
 __device__ __forceinline__ bool epoch_reached(uint32_t have, uint32_t want) {
@@ -27,12 +42,15 @@ __device__ __forceinline__ void wait_epoch(const uint32_t* flag, uint32_t want, 
                                            int idx = -1) {
   if (epoch_reached(ld_acquire_sys(flag), want)) return;
   const uint64_t t0 = global_timer_ns();
+  const unsigned long long limit = g_peer_timeout_ns;
   while (!epoch_reached(ld_acquire_sys(flag), want)) {
-    if (global_timer_ns() - t0 > RFA_WATCHDOG_NS) {
-      printf("rfa: epoch wait timeout (%s) rank %d peer/flag %d block %d want %u have %u\n", what, who, idx,
+    if (limit != 0 && global_timer_ns() - t0 > limit) {
+      printf("rfa: gave up waiting for a peer after %llu s (%s) rank %d peer/flag %d block %d want %u have %u "
+             "(RFA_B200_PEER_TIMEOUT_S raises the limit, 0 disables it)\n", limit / 1000000000ull, what, who, idx,
              blockIdx.x, want, ld_acquire_sys(flag));
       __trap();
     }
+    __nanosleep(64);  // the peer is microseconds to seconds away: do not hammer the memory system while spinning
   }
 }
 
@@ -47,13 +65,37 @@ __device__ __forceinline__ void st_v4(uint4* p, const uint4& v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Task ti of this launch.  Static mode: a row of the host-built table.  Dynamic mode: tasks are enumerated as
+// (ring step, K|V, range, chunk) and cut out of the destination's all-gathered needs; rows == 0 means "nothing to
+// copy" (the task still counts towards the destination's "everything is out" target).
+__device__ __forceinline__ PushTask push_task_at(const PushParams& pp, int ti) {
+  if (pp.tasks != nullptr) return pp.tasks[ti];
+  PushTask t;
+  const int per_dst = 2 * kNeedRanges * pp.dyn_chunks;
+  const int step = ti / per_dst + 1;
+  int rem = ti - (step - 1) * per_dst;
+  t.dst = (pp.my_rank + step) % pp.world;
+  t.which = rem / (kNeedRanges * pp.dyn_chunks);
+  rem -= t.which * (kNeedRanges * pp.dyn_chunks);
+  const int range = rem / pp.dyn_chunks, c = rem - range * pp.dyn_chunks;
+  const int* nd = pp.dyn_needs + ((t.dst * pp.world + pp.my_rank) * kNeedRanges + range) * 2;
+  const int lo = nd[0], hi = nd[1];
+  const long long r0 = static_cast<long long>(lo) + static_cast<long long>(c) * pp.dyn_chunk_rows;
+  const long long n = r0 < hi ? (hi - r0 < pp.dyn_chunk_rows ? hi - r0 : pp.dyn_chunk_rows) : 0;
+  t.rows = static_cast<int>(n);
+  t.src_row = r0;
+  t.dst_off = t.which * pp.region_bytes + (static_cast<long long>(pp.my_rank) * pp.rows_cap + r0) * pp.row_bytes;
+  t.pad = 0;
+  return t;
+}
+
 // Body of a push CTA.  Tasks are sorted by destination in ring order; CTA b takes tasks b, b + n, ...
 __device__ __forceinline__ void push_role(const PushParams& pp) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   __shared__ int s_last;
   for (int ti = blockIdx.x; ti < pp.n_tasks; ti += pp.n_ctas) {
-    const PushTask t = pp.tasks[ti];
-    if (tid == 0 && pp.epoch > 2) {
+    const PushTask t = push_task_at(pp, ti);
+    if (tid == 0 && pp.epoch > 2 && t.rows > 0) {
       // the destination must have finished reading what we pushed into this staging parity two calls ago
       wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse", pp.my_rank, t.dst);
     }
@@ -125,8 +167,9 @@ __device__ __forceinline__ void push_role_tma(const PushParams& pp, uint8_t* sme
   const int rows_per_piece = pp.row_bytes >= kPushBufBytes ? 1 : kPushBufBytes / pp.row_bytes;
   uint32_t n_loaded = 0, n_stored = 0;  // global piece counters (ring position / parity)
   for (int ti = blockIdx.x; ti < pp.n_tasks; ti += pp.n_ctas) {
-    const PushTask t = pp.tasks[ti];
-    if (pp.epoch > 2) wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse", pp.my_rank, t.dst);
+    const PushTask t = push_task_at(pp, ti);
+    if (pp.epoch > 2 && t.rows > 0)
+      wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse", pp.my_rank, t.dst);
     const long long pitch = pp.src_row_bytes[t.which];
     const char* src = pp.src_base[t.which] + t.src_row * pitch;
     char* dst = pp.stage_ptrs[t.dst] + pp.parity_off + t.dst_off;

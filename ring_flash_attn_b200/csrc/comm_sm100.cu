@@ -41,10 +41,10 @@ __device__ __forceinline__ float4 unpack4<__half>(const uint2& a) {
   const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
-__device__ __forceinline__ uint2 ldcv_u2(const uint2* p) {
-  uint2 r;
+__device__ __forceinline__ uint4 ldcv_u4(const uint4* p) {
+  uint4 r;
   // written by a peer over NVLink: always read from L2, never from a stale L1 line
-  asm volatile("ld.global.cv.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 
@@ -54,50 +54,76 @@ __device__ __forceinline__ uint2 ldcv_u2(const uint2* p) {
 template <typename T>
 __global__ void __launch_bounds__(256) reduce_dkv_kernel(const __grid_constant__ ReduceParams p) {
   const ReduceTask t = p.tasks[blockIdx.y];
+  // dynamic mode: which rows of my shard rank s returns = the rows it read = needs[s][me] (all-gathered table)
+  __shared__ int s_need[kMaxRanks][kNeedRanges][2];
+  const bool dyn = p.dyn_needs != nullptr;
+  if (dyn) {
+    for (int i = threadIdx.x; i < p.world * kNeedRanges * 2; i += blockDim.x) {
+      const int s = i / (kNeedRanges * 2), j = i - s * (kNeedRanges * 2);
+      (&s_need[s][0][0])[j] = p.dyn_needs[(s * p.world + p.my_rank) * kNeedRanges * 2 + j];
+    }
+    __syncthreads();
+  }
+  auto dyn_mask = [&](int row) {
+    unsigned m = 0;
+    for (int s = 0; s < p.world; ++s)
+#pragma unroll
+      for (int j = 0; j < kNeedRanges; ++j)
+        if (row >= s_need[s][j][0] && row < s_need[s][j][1]) m |= 1u << s;
+    return m;
+  };
   if (threadIdx.x == 0) {
     for (int r = 0; r < p.world; ++r) {
-      if ((t.src_mask >> r) & 1u) {
-        if (r != p.my_rank) wait_epoch(p.my_pad + kPadDkvReady + r, p.epoch, "dkv landed", p.my_rank, r);
+      bool contributes = (t.src_mask >> r) & 1u;
+      if (dyn) {
+        contributes = false;
+        for (int j = 0; j < kNeedRanges; ++j) contributes |= s_need[r][j][1] > s_need[r][j][0];
       }
+      if (contributes && r != p.my_rank) wait_epoch(p.my_pad + kPadDkvReady + r, p.epoch, "dkv landed", p.my_rank, r);
     }
   }
   __syncthreads();
-  const long long n4 = static_cast<long long>(t.rows) * p.row_elems / 4;
-  const long long off4 = static_cast<long long>(t.row0) * p.row_elems / 4;
-  const long long slot4 = p.slot_stride / 4;
+  // 8 elements (16 bytes) per access; rows are multiples of 128 elements, so a vector never straddles a row
+  const long long n8 = static_cast<long long>(t.rows) * p.row_elems / 8;
+  const long long off8 = static_cast<long long>(t.row0) * p.row_elems / 8;
+  const long long slot8 = p.slot_stride / 8;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   constexpr int U = 4;
   for (int which = 0; which < 2; ++which) {
-    const uint2* in = reinterpret_cast<const uint2*>(static_cast<const T*>(p.inbox) + which * p.kv_stride) + off4;
-    uint2* out = reinterpret_cast<uint2*>(which == 0 ? p.dk : p.dv) + off4;
-    for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
-      float4 acc[U];
+    const uint4* in = reinterpret_cast<const uint4*>(static_cast<const T*>(p.inbox) + which * p.kv_stride) + off8;
+    uint4* out = reinterpret_cast<uint4*>(which == 0 ? p.dk : p.dv) + off8;
+    for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n8; i0 += stride * U) {
+      float4 acc[U][2];
+      unsigned mask[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < U; ++u) {
+        acc[u][0] = acc[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mask[u] = t.src_mask;
+        if (dyn) mask[u] = dyn_mask(t.row0 + static_cast<int>((i0 + u * stride) * 8 / p.row_elems));
+      }
       for (int r = 0; r < p.world; ++r) {
-        if (!((t.src_mask >> r) & 1u)) continue;
-        uint2 v[U];
+        if (!dyn && !((t.src_mask >> r) & 1u)) continue;
+        uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long i = i0 + u * stride;
-          if (i < n4) v[u] = ldcv_u2(in + r * slot4 + i);
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < n8 && ((mask[u] >> r) & 1u)) v[u] = ldcv_u4(in + r * slot8 + i);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const long long i = i0 + u * stride;
-          if (i < n4) {
-            const float4 f = unpack4<T>(v[u]);
-            acc[u].x += f.x;
-            acc[u].y += f.y;
-            acc[u].z += f.z;
-            acc[u].w += f.w;
-          }
+          const float4 lo = unpack4<T>(make_uint2(v[u].x, v[u].y)), hi = unpack4<T>(make_uint2(v[u].z, v[u].w));
+          acc[u][0].x += lo.x; acc[u][0].y += lo.y; acc[u][0].z += lo.z; acc[u][0].w += lo.w;
+          acc[u][1].x += hi.x; acc[u][1].y += hi.y; acc[u][1].z += hi.z; acc[u][1].w += hi.w;
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long i = i0 + u * stride;
-        if (i < n4) out[i] = pack4<T>(acc[u]);
+        if (i < n8) {
+          const uint2 lo = pack4<T>(acc[u][0]), hi = pack4<T>(acc[u][1]);
+          out[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        }
       }
     }
   }
@@ -131,6 +157,7 @@ __global__ void __launch_bounds__(256) dq_finalize_kernel(float4* __restrict__ a
 
 const char* reduce_dkv_launch(int dtype, const ReduceParams& p, cudaStream_t stream) {
   if (p.n_tasks <= 0) return nullptr;
+  set_peer_timeout_from_env();
   dim3 grid(kReduceBlocksPerTask, p.n_tasks, 1);
   if (dtype == kDtypeBF16) {
     comm::reduce_dkv_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);

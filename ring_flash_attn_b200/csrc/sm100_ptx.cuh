@@ -11,10 +11,16 @@
 namespace rfa {
 
 #ifndef RFA_WATCHDOG_NS
-// Bounded waits turn a protocol bug into a trap (an error) instead of a hung GPU: 20 s of wall time
-// (cross-GPU waits must tolerate a peer that is late by a lazy module load or a host hiccup).
+// Bounded waits turn a protocol bug into a trap (an error) instead of a hung GPU.  This constant bounds the waits
+// INSIDE a CTA (mbarriers between its own warps): 20 s of wall time is far beyond anything legitimate there.
+// Waits on ANOTHER GPU (epoch flags, comm_device.cuh:wait_epoch) have their own, much longer, run-time limit
+// (g_peer_timeout_ns below): a peer may legitimately be late by a checkpoint, a dataloader stall or a recompile.
 #define RFA_WATCHDOG_NS 20000000000ull
 #endif
+
+// Limit of cross-GPU waits in nanoseconds, one copy per translation unit, set by the launchers from
+// RFA_B200_PEER_TIMEOUT_S (default 600 s = NCCL's default watchdog); 0 = wait forever.
+static __device__ unsigned long long g_peer_timeout_ns = 600000000000ull;
 
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;

@@ -64,9 +64,11 @@ def _ring_core(query_states, key_states, value_states, *, is_causal, dropout, so
         raise RuntimeError("call update_ring_flash_attn_params(cu_seqlens, group) before the model forward")
     window = (-1, -1)
     if sliding_window is not None and DATA_PARAMS["max_seqlen_k"] > sliding_window:
-        # transformers' convention (modeling_flash_attention_utils.py: window_size = (w - 1, w - 1)): a token
-        # sees itself and the w - 1 tokens before it.  The window is applied to global positions in the
-        # document, whichever rank holds the keys.
+        # transformers' convention since 4.4x and in the installed 5.x (modeling_flash_attention_utils.py:
+        # window_size = (w - 1, w - 1)): a token sees itself and the w - 1 tokens before it.  The reference adapter
+        # passes (w, w) (/root/reference/ring_flash_attn/adapters/hf_adapter.py:121-130), the convention of the
+        # transformers releases it was written against - one more key than today's HF models attend to.  The
+        # window is applied to global positions in the document, whichever rank holds the keys.
         window = (int(sliding_window) - 1, 0)
     if deterministic is None:
         deterministic = os.environ.get("FLASH_ATTENTION_DETERMINISTIC", "0") == "1"
@@ -178,8 +180,13 @@ def substitute_hf_flash_attn(process_group: Optional[dist.ProcessGroup], heads_k
     switchable.__wrapped__ = old
     fau._flash_attention_forward = switchable
     # modules that did `from ..modeling_flash_attention_utils import _flash_attention_forward`
+    # (also modules still bound to the closure of an EARLIER substitute call - recognisable by __wrapped__ - so that
+    # a second call with another process group / heads_k_stride / layout takes effect everywhere)
     for name, mod in list(sys.modules.items()):
-        if name.startswith("transformers.") and mod is not fau and getattr(mod, "_flash_attention_forward", None) is old:
+        if not name.startswith("transformers.") or mod is fau:
+            continue
+        cur = getattr(mod, "_flash_attention_forward", None)
+        if cur is old or (cur is not None and getattr(cur, "__wrapped__", None) is old):
             setattr(mod, "_flash_attention_forward", switchable)
 
     try:
@@ -207,7 +214,8 @@ def restore_hf_flash_attn() -> None:
         cur = fau._flash_attention_forward
         fau._flash_attention_forward = old
         for name, mod in list(sys.modules.items()):
-            if name.startswith("transformers.") and getattr(mod, "_flash_attention_forward", None) is cur:
+            have = getattr(mod, "_flash_attention_forward", None) if name.startswith("transformers.") else None
+            if have is not None and (have is cur or getattr(have, "__wrapped__", None) is old):
                 setattr(mod, "_flash_attention_forward", old)
     stock = _ORIGINALS.get("interface_fa2")
     if stock is not None:

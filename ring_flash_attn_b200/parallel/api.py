@@ -18,9 +18,9 @@ from typing import Optional, Tuple
 
 import torch
 
-from ..ops import plan as P
-from . import engine
+from . import ops as O
 from .comm import group_info
+from .ops import cu_seqlens_to_host  # noqa: F401  (re-exported: models/hf_adapter.py, tests)
 
 __all__ = [
     "ring_flash_attn_func", "ring_flash_attn_kvpacked_func", "ring_flash_attn_qkvpacked_func",
@@ -38,28 +38,8 @@ __all__ = [
 
 
 # ----------------------------------------------------------------------------------------------
-# autograd bridge
+# the op: one torch.library custom op for every scheme (parallel/ops.py)
 # ----------------------------------------------------------------------------------------------
-
-class CPAttention(torch.autograd.Function):
-    """One bridge for every scheme.  Inputs are token-major: q (T,Hq,D), k/v (T,Hkv,D)."""
-
-    @staticmethod
-    def forward(ctx, q, k, v, plan, scale, group, transport, heads_k_stride, deterministic):
-        out, lse = engine.cp_forward(plan, q, k, v, scale, group, transport, heads_k_stride)
-        ctx.save_for_backward(q, k, v, out, lse)
-        ctx.plan, ctx.scale, ctx.group = plan, scale, group
-        ctx.transport, ctx.heads_k_stride, ctx.deterministic = transport, heads_k_stride, deterministic
-        ctx.mark_non_differentiable(lse)
-        return out, lse
-
-    @staticmethod
-    def backward(ctx, dout, _dlse):
-        q, k, v, out, lse = ctx.saved_tensors
-        dq, dk, dv = engine.cp_backward(ctx.plan, dout, q, k, v, out, lse, ctx.scale, ctx.group,
-                                        ctx.transport, ctx.heads_k_stride, ctx.deterministic)
-        return dq, dk, dv, None, None, None, None, None, None
-
 
 KERNEL_HEAD_DIM = 128  # the sm_100a kernels are specialised for this head size
 
@@ -85,27 +65,28 @@ def _pad_head_dim(q) -> int:
     return 0
 
 
-def _cp_apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic, fp8=None):
-    if fp8 is not None:
-        # experimental fp8 forward: e4m3 q / k / v straight into the kernels (and over the wire), bf16 out.
-        # Forward only - fp8 tensors carry no gradient.
-        from ..ops import attn_cuda
+def _cp_apply(q, k, v, scheme, spec, cu_a, cu_b, scale, group, deterministic, fp8=None):
+    """Token-major q (T,Hq,D), k / v (T,Hkv,D) -> (out, lse) through ``torch.ops.rfa_b200.cp_attn_fwd``.
 
-        with attn_cuda.fp8_scales(*fp8), torch.no_grad():
-            return engine.cp_forward(plan, q, k, v, scale, group, transport, heads_k_stride)
+    Everything here is traceable by dynamo (shapes, strings, ints); plans, cu_seqlens reads, peer memory and the
+    launches live inside the op, so ``torch.compile(fullgraph=True)`` works on the public functions."""
+    gname = O.group_name(group)
+    if fp8 is not None:
+        # fp8 forward kernel: e4m3 q / k / v straight into the kernels (and over the wire), bf16 out.
+        # Forward only - fp8 tensors carry no gradient.
+        with torch.no_grad():
+            return O.cp_attn_fwd(q, k, v, cu_a, cu_b, fp8[0], fp8[1], scheme, gname, spec, scale, deterministic)
     pad = _pad_head_dim(q)
     if pad:
         d = q.shape[-1]
         q, k, v = (torch.nn.functional.pad(t, (0, pad)) for t in (q, k, v))
-        out, lse = CPAttention.apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic)
+        out, lse = O.cp_attn_fwd(q, k, v, cu_a, cu_b, None, None, scheme, gname, spec, scale, deterministic)
         return out[..., :d].contiguous(), lse
-    return CPAttention.apply(q, k, v, plan, scale, group, transport, heads_k_stride, deterministic)
+    return O.cp_attn_fwd(q, k, v, cu_a, cu_b, None, None, scheme, gname, spec, scale, deterministic)
 
 
-try:  # torch.compile: treat the op as an opaque eager call (plans, peer memory and launches are host code)
-    _cp_apply = torch.compiler.disable(_cp_apply)
-except AttributeError:  # pragma: no cover - very old torch
-    pass
+def _as_cu_tensor(cu) -> torch.Tensor:
+    return cu if isinstance(cu, torch.Tensor) else torch.tensor([int(x) for x in cu], dtype=torch.int32)
 
 
 def _per_head(descale, x) -> Optional[torch.Tensor]:
@@ -184,85 +165,9 @@ def _scale(q, softmax_scale):
     return q.shape[-1] ** (-0.5) if softmax_scale is None else float(softmax_scale)
 
 
-# The llama3 entry point only receives this rank's slice description; different global layouts can produce the
-# SAME local description on some rank, so prepare() attaches the global cu_seqlens to the tensor objects it
-# returns (attribute `_rfa_llama3`) and the entry point reads it back from the tensors the caller passes in.
-# It lets a rank derive its peers' plans locally - the fused path must know which K/V rows each peer wants.
-
-
-def cu_seqlens_to_host(cu: torch.Tensor) -> Tuple[int, ...]:
-    """Host copy of a cu_seqlens tensor.  A device tensor is read back once; the result is remembered ON the
-    tensor object together with its version counter (never keyed by address: the caching allocator hands the
-    same address to the next batch's cu_seqlens)."""
-    if not isinstance(cu, torch.Tensor):
-        return tuple(int(x) for x in cu)
-    if cu.device.type == "cpu":
-        return tuple(int(x) for x in cu.tolist())
-    cached = getattr(cu, "_rfa_host", None)
-    if cached is not None and cached[0] == cu._version:
-        return cached[1]
-    vals = tuple(int(x) for x in cu.tolist())
-    try:
-        cu._rfa_host = (cu._version, vals)
-    except AttributeError:  # pragma: no cover - exotic tensor subclasses
-        pass
-    return vals
-
-
 def _window(window_size) -> Tuple[int, int]:
     left, right = (int(x) for x in window_size)
     return (-1 if left < 0 else left, -1 if right < 0 else right)
-
-
-# Plans are cached per (scheme, rank, shapes, ...).  Each plan also knows how to produce its peers' plans
-# (``plan.peer(r)``): the fused path derives from them which K/V rows every peer needs and which dK/dV rows every
-# peer will send back, without any exchange at run time.
-
-@functools.lru_cache(maxsize=512)
-def _batch_plan(scheme, rank, world, batch, seqlen, causal, window=(-1, -1)):
-    if scheme == "ring":
-        plan = P.plan_ring(rank, world, batch, seqlen, causal, window)
-    elif scheme == "zigzag":
-        plan = P.plan_zigzag(rank, world, batch, seqlen, window)
-    elif scheme == "stripe":
-        plan = P.plan_stripe(rank, world, batch, seqlen, window)
-    else:
-        raise ValueError(scheme)
-    plan.peer = lambda r: _batch_plan(scheme, r, world, batch, seqlen, causal, window)
-    return plan
-
-
-@functools.lru_cache(maxsize=512)
-def _varlen_plan(scheme, rank, world, cu, causal, window=(-1, -1)):
-    if scheme == "ring":
-        plan = P.plan_ring_varlen(rank, world, cu, causal, window)
-    elif scheme == "zigzag":
-        plan = P.plan_zigzag_varlen(rank, world, cu, window)
-    else:
-        raise ValueError(scheme)
-    plan.peer = lambda r: _varlen_plan(scheme, r, world, cu, causal, window)
-    return plan
-
-
-@functools.lru_cache(maxsize=512)
-def _zigzag_llama3_plan(rank, world, global_cu, causal, window=(-1, -1)):
-    plan = P.plan_zigzag_llama3(rank, world, global_cu, causal, window)
-    plan.peer = lambda r: _zigzag_llama3_plan(r, world, global_cu, causal, window)
-    return plan
-
-
-@functools.lru_cache(maxsize=512)
-def _llama3_plan(rank, world, tokens, cu_q, cu_k, k_start, causal, global_cu=None, window=(-1, -1)):
-    # global_cu is part of the cache key on purpose: plans with equal local content but different global
-    # layouts must not share their per-plan caches (peers' needs, push tables)
-    plan = P.plan_llama3(rank, world, tokens, cu_q, cu_k, k_start, causal, window)
-    if global_cu is not None:
-        plan.peer = lambda r: _llama3_peer_plan(global_cu, causal, r, world, tokens, window)
-    elif world > 1:
-        # global layout unknown (cu tensors not produced by prepare()): the peers' needs cannot be derived
-        # locally, so such calls use the torch.distributed all-gather transport around the same kernels
-        plan.fused_ok = False
-    return plan
 
 
 def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes,
@@ -271,13 +176,11 @@ def _run_batch(scheme, q, k, v, dropout_p, softmax_scale, causal, window_size, a
     q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
     if scheme in ("zigzag", "stripe") and not causal:
         raise AssertionError(f"{scheme} attention only supports causal=True (as in the reference)")
-    rank, world = group_info(group)
     b, s, hq, d = q.shape
-    win = _window(window_size)
-    plan = _batch_plan(scheme, rank, world, b, s, bool(causal), win)
-    out, lse = _cp_apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d),
-                                 v.reshape(b * s, v.shape[2], d), plan, _scale(q, softmax_scale), group,
-                                 "ring", 1, deterministic, fp8)
+    wl, wr = _window(window_size)
+    out, lse = _cp_apply(q.reshape(b * s, hq, d), k.reshape(b * s, k.shape[2], d), v.reshape(b * s, v.shape[2], d),
+                         scheme, [b, s, int(bool(causal)), wl, wr], None, None, _scale(q, softmax_scale), group,
+                         bool(deterministic), fp8)
     out = out.view(b, s, hq, d)
     if not return_attn_probs:
         return out
@@ -290,13 +193,9 @@ def _run_varlen(scheme, q, k, v, cu_seqlens, max_seqlen, dropout_p, softmax_scal
     q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
     if scheme == "zigzag" and not causal:
         raise AssertionError("zigzag attention only supports causal=True (as in the reference)")
-    rank, world = group_info(group)
-    cu_host = cu_seqlens_to_host(cu_seqlens)
-    win = _window(window_size)
-    plan = _varlen_plan(scheme, rank, world, cu_host, bool(causal), win)
-    if plan.q_rows != q.shape[0]:
-        raise ValueError(f"cu_seqlens[-1]={plan.q_rows} does not match the {q.shape[0]} local tokens")
-    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic, fp8)
+    wl, wr = _window(window_size)
+    out, lse = _cp_apply(q, k, v, scheme + "_varlen", [int(bool(causal)), wl, wr], _as_cu_tensor(cu_seqlens), None,
+                         _scale(q, softmax_scale), group, bool(deterministic), fp8)
     return (out, lse, None) if return_attn_probs else out
 
 
@@ -417,21 +316,11 @@ def llama3_flash_attn_prepare_cu_seqlens(cu_seqlens: torch.Tensor, causal: bool,
     dt = cu_seqlens.dtype if isinstance(cu_seqlens, torch.Tensor) else torch.int32
     cu_q_t = torch.tensor(cu_q, dtype=dt, device=dev)
     cu_k_t = torch.tensor(cu_k, dtype=dt, device=dev)
-    cu_q_t._rfa_host = (cu_q_t._version, tuple(cu_q))
+    cu_q_t._rfa_host = (cu_q_t._version, tuple(cu_q))  # saves the entry point one device read (optional)
     cu_k_t._rfa_host = (cu_k_t._version, tuple(cu_k))
-    # remember the global layout ON the returned tensor objects (see _LLAMA3_GLOBAL note above)
-    cu_q_t._rfa_llama3 = cu_k_t._rfa_llama3 = (tuple(cu), tuple(cu_q), tuple(cu_k), rank, world_size, bool(causal))
     max_q = max(b - a for a, b in zip(cu_q[:-1], cu_q[1:]))
     max_k = max(b - a for a, b in zip(cu_k[:-1], cu_k[1:]))
     return cu_q_t, cu_k_t, max_q, max_k, slice(slice_left, slice_right)
-
-
-@functools.lru_cache(maxsize=512)
-def _llama3_peer_plan(global_cu, causal, rank, world, tokens, window=(-1, -1)):
-    cq, ck, _mq, _mk, ks = llama3_flash_attn_prepare_cu_seqlens(torch.tensor(global_cu, dtype=torch.int32), causal,
-                                                               rank, world)
-    return _llama3_plan(rank, world, tokens, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), causal, global_cu,
-                        window)
 
 
 def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
@@ -442,18 +331,13 @@ def llama3_flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqle
     cu_seqlens / local_k_slice come from :func:`llama3_flash_attn_prepare_cu_seqlens`."""
     _check_common(q, dropout_p, window_size, alibi_slopes)
     q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
-    rank, world = group_info(group)
-    k_start = local_k_slice.start or 0
-    cu_q_host, cu_k_host = cu_seqlens_to_host(cu_seqlens_q), cu_seqlens_to_host(cu_seqlens_k)
-    glob = None
-    hit = getattr(cu_seqlens_q, "_rfa_llama3", None)
-    if hit is not None and hit is getattr(cu_seqlens_k, "_rfa_llama3", None) and \
-            hit[1:] == (cu_q_host, cu_k_host, rank, world, bool(causal)):
-        glob = hit[0]
-    plan = _llama3_plan(rank, world, q.shape[0], cu_q_host, cu_k_host, int(k_start), bool(causal), glob,
-                        _window(window_size))
-    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "allgather",
-                                 int(heads_k_stride), deterministic, fp8)
+    k_start = int(local_k_slice.start or 0)
+    wl, wr = _window(window_size)
+    # any valid (cu_seqlens_q, cu_seqlens_k, local_k_slice) stays on the fused path: what each peer needs of this
+    # rank's K/V is learnt from the peers at run time (parallel/symm.py), not from attributes of these tensors
+    out, lse = _cp_apply(q, k, v, "llama3", [k_start, int(bool(causal)), wl, wr, int(heads_k_stride)],
+                         _as_cu_tensor(cu_seqlens_q), _as_cu_tensor(cu_seqlens_k), _scale(q, softmax_scale), group,
+                         bool(deterministic), fp8)
     return (out, lse, None) if return_attn_probs else out
 
 
@@ -501,13 +385,9 @@ def zigzag_llama3_flash_attn_varlen_func(q, k, v, cu_seqlens, dropout_p=0.0, sof
     q (T_local, Hq, D), k / v (T_local, Hkv, D); returns out (and (out, lse (Hq, T_local), None))."""
     _check_common(q, dropout_p, window_size, alibi_slopes)
     q, k, v, fp8 = _maybe_dequant(q, k, v, descale, window_size)
-    rank, world = group_info(group)
-    cu_host = cu_seqlens_to_host(cu_seqlens)
-    if cu_host[-1] != q.shape[0] * world:
-        raise ValueError(f"cu_seqlens[-1]={cu_host[-1]} must equal local tokens ({q.shape[0]}) x world size ({world}): "
-                         "this entry point takes the GLOBAL cu_seqlens")
-    plan = _zigzag_llama3_plan(rank, world, cu_host, bool(causal), _window(window_size))
-    out, lse = _cp_apply(q, k, v, plan, _scale(q, softmax_scale), group, "ring", 1, deterministic, fp8)
+    wl, wr = _window(window_size)
+    out, lse = _cp_apply(q, k, v, "zigzag_llama3", [int(bool(causal)), wl, wr], _as_cu_tensor(cu_seqlens), None,
+                         _scale(q, softmax_scale), group, bool(deterministic), fp8)
     return (out, lse, None) if return_attn_probs else out
 
 

@@ -298,11 +298,32 @@ def _fused_ok(q: torch.Tensor, k: torch.Tensor, group, plan=None) -> bool:
         return False
     if q.element_size() == 1 and os.environ.get("RFA_B200_FP8_KERNEL", "2") == "1":
         return False  # =1: fp8 kernel on the per-source transports only (e4m3 over NCCL), not inside the fused launch
-    if plan is not None and (not getattr(plan, "fused_ok", True) or not _kernels_take(plan)):
+    if plan is not None and not _kernels_take(plan):
         return False
     from . import fused
 
-    return fused.available(q, group)
+    if not fused.available(q, group):
+        return False
+    if plan is not None and plan.world > 1:
+        from . import symm
+
+        if symm.is_dynamic(plan) and not symm.dynamic_ok(plan):
+            _warn_once("plan reads more than %d separate row ranges of one source shard: using the "
+                       "torch.distributed transport instead of the fused NVLink path" % symm.NEED_RANGES)
+            return False
+    return True
+
+
+_WARNED = set()
+
+
+def _warn_once(msg: str) -> None:
+    """Falling off the fused path is a performance cliff: say so, once per distinct reason."""
+    if msg not in _WARNED:
+        _WARNED.add(msg)
+        import warnings
+
+        warnings.warn("ring_flash_attn_b200: " + msg, RuntimeWarning, stacklevel=3)
 
 
 def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_stride: int = 1):
@@ -317,6 +338,11 @@ def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_st
 
 def cp_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, transport="ring",
                 heads_k_stride: int = 1, deterministic: bool = False):
+    if deterministic and _use_cuda_kernels(q, k) and _kernels_take(plan):
+        # the reference forwards the flag to flash-attn's backward (ring_flash_attn.py:119); here dK / dV have one
+        # writer per tile and a fixed-order owner-side sum, but dQ tiles are added with unordered fp32 L2 reductions
+        _warn_once("deterministic=True: dK / dV are bitwise reproducible on the sm_100a path, dQ is accumulated "
+                   "with fp32 reductions whose order is not fixed (run-to-run differences of ~1 ulp of fp32)")
     if _fused_ok(q, k, group, plan):
         from . import fused
 

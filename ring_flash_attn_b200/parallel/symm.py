@@ -33,7 +33,7 @@ from .comm import group_info
 
 PAD_WORDS = 1024
 MASK32 = 0xFFFFFFFF
-_CONTEXTS: Dict[Tuple[int, int], Optional["PeerContext"]] = {}
+_CONTEXTS: Dict[Tuple[str, int], Optional["PeerContext"]] = {}
 
 
 class PeerBuffer:
@@ -116,8 +116,23 @@ class PeerContext:
         self.inbox = PeerBuffer(need, self.device, self.group)
         self._quiesce()
 
+    # -- host-side protocol state --------------------------------------------------------------------
+    # The cumulative targets below are advanced BEFORE a launch (the launch needs them); if the launch then fails
+    # on the host (a TORCH_CHECK, an invalid configuration) the device counters never moved, and the next call of
+    # every rank would wait for epochs that are never reached.  Callers snapshot / restore around the launch.
+    _STATE = ("epoch", "last_bwd_epoch", "done_cum", "ticket_cum")
+
+    def snapshot(self):
+        return ({n: getattr(self, n) for n in self._STATE}, list(self.sent_cum), list(self.dkv_cum))
+
+    def restore(self, snap) -> None:
+        scalars, sent, dkv = snap
+        for n, v in scalars.items():
+            setattr(self, n, v)
+        self.sent_cum, self.dkv_cum = list(sent), list(dkv)
+
     # -- per-call context object --------------------------------------------------------------------
-    def fused_ctx(self, plan: CPPlan, k: torch.Tensor, n_compute_ctas: int):
+    def fused_ctx(self, plan: CPPlan, k: torch.Tensor, n_compute_ctas: int, dyn_needs: Optional[torch.Tensor] = None):
         C = cuda_ext.load()
         rows, hkv = plan.kv_rows, k.shape[1]
         esize = k.element_size()
@@ -130,7 +145,19 @@ class PeerContext:
         fc.k_stage = self.stage.tensor(half, (self.world * rows, hkv, 128), k.dtype)
         fc.v_stage = self.stage.tensor(half + region, (self.world * rows, hkv, 128), k.dtype)
         fc.my_pad = self.pad_tensor
-        tasks, per_dst = push_tasks(plan, self, row_bytes, k.device)
+        fc.rows_cap, fc.region_bytes = rows, region
+        if dyn_needs is None:
+            tasks, per_dst = push_tasks(plan, self, row_bytes, k.device)
+            n_tasks = int(tasks.shape[0])
+        else:
+            # the peers' needs only exist on the device (needs_gathered): the push CTAs cut their tasks out of the
+            # table themselves; every (destination, K|V, range, chunk) counts, copied rows or not
+            tasks = torch.zeros((0, 4), dtype=torch.int64, device=k.device)
+            chunk = push_chunk_rows(row_bytes)
+            chunks = -(-rows // chunk)
+            fc.dyn_needs, fc.dyn_chunk_rows, fc.dyn_chunks = dyn_needs, chunk, chunks
+            per_dst = [0 if d == self.rank else 2 * NEED_RANGES * chunks for d in range(self.world)]
+            n_tasks = sum(per_dst)
         fc.push_tasks = tasks
         fc.counters = self.counters
         fc.stage_ptrs = list(self.stage.ptrs)
@@ -138,7 +165,7 @@ class PeerContext:
         for d in range(self.world):
             self.sent_cum[d] = (self.sent_cum[d] + per_dst[d]) & MASK32
         fc.sent_targets = list(self.sent_cum)
-        fc.n_push_ctas = min(self.n_push_ctas, int(tasks.shape[0])) if tasks.shape[0] else 0
+        fc.n_push_ctas = min(self.n_push_ctas, n_tasks) if n_tasks else 0
         fc.row_bytes = row_bytes
         fc.my_rank = self.rank
         fc.world = self.world
@@ -164,7 +191,9 @@ def destroy_peer_contexts() -> None:
 
 def peer_context(group, device: torch.device) -> Optional[PeerContext]:
     """The context for (group, device), created collectively on first use; None if P2P is unavailable."""
-    key = (id(group) if group is not None else 0, device.index)
+    # keyed by the group's c10d NAME (unique for the life of the process; id(group) can be reused by a new group
+    # after the old one is destroyed, which would hand it stale IPC mappings and epochs)
+    key = (str(group.group_name) if group is not None else "", device.index)
     if key in _CONTEXTS:
         return _CONTEXTS[key]
     rank, world = group_info(group)
@@ -184,27 +213,85 @@ def peer_context(group, device: torch.device) -> Optional[PeerContext]:
 # ----------------------------------------------------------------------------------------------
 # who needs what
 # ----------------------------------------------------------------------------------------------
+NEED_RANGES = 4  # csrc/attn_common.h: kNeedRanges
+
 
 def needs_matrix(plan: CPPlan, group) -> List[List[List[Tuple[int, int]]]]:
-    """needs[dst][src] = list of [lo, hi) row ranges of src's shard that dst's plan reads.
-
-    Derived locally from the plan family when the scheme is position-based; exchanged once over the
-    process group otherwise (llama3 layouts whose global cu_seqlens this rank never saw)."""
+    """needs[dst][src] = list of [lo, hi) row ranges of src's shard that dst's plan reads, derived locally from the
+    plan family (position-based schemes: every rank can build every peer's plan)."""
     cached = getattr(plan, "_needs", None)
     if cached is not None:
         return cached
     world = plan.world
-    peer = getattr(plan, "peer", None)
-    if peer is not None:
-        fam = [plan if r == plan.rank else peer(r) for r in range(world)]
-        needs = [[_ranges(fam[d], s) for s in range(world)] for d in range(world)]
-    else:
-        mine = [_ranges(plan, s) for s in range(world)]
-        gathered: List[Optional[list]] = [None] * world
-        dist.all_gather_object(gathered, mine, group=group)
-        needs = gathered
+    fam = [plan if r == plan.rank else plan.peer(r) for r in range(world)]
+    needs = [[_ranges(fam[d], s) for s in range(world)] for d in range(world)]
     plan._needs = needs
     return needs
+
+
+def is_dynamic(plan: CPPlan) -> bool:
+    """Plans that cannot derive their peers' plans (llama3: a rank only sees its own slice of the global
+    cu_seqlens).  Which rows every peer needs is then exchanged on the DEVICE right before each launch."""
+    return plan.world > 1 and getattr(plan, "peer", None) is None
+
+
+def dynamic_ok(plan: CPPlan) -> bool:
+    """The device-side needs table holds NEED_RANGES row ranges per source."""
+    return all(len(_ranges(plan, s)) <= NEED_RANGES for s in range(plan.world))
+
+
+def local_needs_table(plan: CPPlan) -> torch.Tensor:
+    """int32 (world src, NEED_RANGES, 2): the [lo, hi) row ranges of every source's shard this rank's plan reads."""
+    table = torch.zeros((plan.world, NEED_RANGES, 2), dtype=torch.int32)
+    for s in range(plan.world):
+        for j, (lo, hi) in enumerate(_ranges(plan, s)):
+            table[s, j, 0], table[s, j, 1] = lo, hi
+    return table
+
+
+def dynamic_push_task(needs_all, me: int, world: int, ti: int, chunk_rows: int, chunks: int, rows_cap: int,
+                      row_bytes: int, region: int):
+    """Host mirror of ``push_task_at`` (csrc/comm_device.cuh) for tests: (src_row, dst_off, rows, dst, which)."""
+    per_dst = 2 * NEED_RANGES * chunks
+    step = ti // per_dst + 1
+    rem = ti - (step - 1) * per_dst
+    dst = (me + step) % world
+    which = rem // (NEED_RANGES * chunks)
+    rem -= which * NEED_RANGES * chunks
+    rng, c = rem // chunks, rem % chunks
+    lo, hi = int(needs_all[dst][me][rng][0]), int(needs_all[dst][me][rng][1])
+    r0 = lo + c * chunk_rows
+    rows = min(chunk_rows, hi - r0) if r0 < hi else 0
+    return r0, which * region + (me * rows_cap + r0) * row_bytes, rows, dst, which
+
+
+def dynamic_row_mask(needs_all, me: int, world: int, row: int) -> int:
+    """Host mirror of the reduce kernel's ``dyn_mask``: bit s set iff rank s returns dK/dV for ``row`` of my shard."""
+    m = 0
+    for s in range(world):
+        if any(int(lo) <= row < int(hi) for lo, hi in needs_all[s][me]):
+            m |= 1 << s
+    return m
+
+
+def needs_gathered(plan: CPPlan, ctx: "PeerContext", device) -> torch.Tensor:
+    """int32 (world dst, world src, NEED_RANGES, 2) on the device: one small all-gather on the current stream per
+    launch, no host synchronisation (the result is only ever read by the kernels that follow in stream order).
+
+    It runs on EVERY call on purpose: two global layouts can give one rank the same local slice description (so
+    that rank could reuse a cached answer) while its peers see different ones - a "gather only when my plan is
+    new" rule would make the ranks disagree about whether a collective happens."""
+    cache = attn_cuda._cache(plan)
+    key = ("needs_local", device.index)
+    if key not in cache:
+        cache[key] = local_needs_table(plan).to(device)
+    out = torch.empty((plan.world, plan.world, NEED_RANGES, 2), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(out, cache[key], group=ctx.group)
+    return out
+
+
+def push_chunk_rows(row_bytes: int) -> int:
+    return max(16, (1 << 19) // row_bytes)  # ~512 KB per push task
 
 
 def _ranges(plan: CPPlan, src: int) -> List[Tuple[int, int]]:
@@ -226,7 +313,7 @@ def push_tasks(plan: CPPlan, ctx: PeerContext, row_bytes: int, device):
         return cache[key]
     needs = needs_matrix(plan, ctx.group)
     me, world, rows = plan.rank, plan.world, plan.kv_rows
-    chunk = max(16, (1 << 19) // row_bytes)  # ~512 KB per task
+    chunk = push_chunk_rows(row_bytes)
     region = world * rows * row_bytes
     table, per_dst = [], [0] * world
     for step in range(1, world):
@@ -273,19 +360,25 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
         items, segs, seg_lo, covered = cache[key]
     else:
         items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, offsets, q.device, ("fused",), flags)
-    fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hq)
+    dyn = needs_gathered(plan, ctx, q.device) if is_dynamic(plan) else None
     tq = q.shape[0]
     out = (torch.empty if covered else torch.zeros)((tq, hq, 128), dtype=attn_cuda.out_dtype(q), device=q.device)
     lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
     if not covered:
         lse.fill_(float("-inf"))
-    if attn_cuda.is_fp8_kernel_input(q, k):
-        sq, sv = attn_cuda.current_fp8_scales()
-        C.attn_fwd_fused_fp8(attn_cuda._rows3(q), k, v, items, segs, sq, sv, out, lse, tq, float(scale), fc)
-    elif window:
-        C.attn_fwd_fused_window(attn_cuda._rows3(q), k, v, items, segs, seg_lo, out, lse, tq, float(scale), fc)
-    else:
-        C.attn_fwd_fused(attn_cuda._rows3(q), k, v, items, segs, out, lse, tq, float(scale), fc)
+    snap = ctx.snapshot()
+    try:
+        fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hq, dyn)
+        if attn_cuda.is_fp8_kernel_input(q, k):
+            sq, sv = attn_cuda.current_fp8_scales()
+            C.attn_fwd_fused_fp8(attn_cuda._rows3(q), k, v, items, segs, sq, sv, out, lse, tq, float(scale), fc)
+        elif window:
+            C.attn_fwd_fused_window(attn_cuda._rows3(q), k, v, items, segs, seg_lo, out, lse, tq, float(scale), fc)
+        else:
+            C.attn_fwd_fused(attn_cuda._rows3(q), k, v, items, segs, out, lse, tq, float(scale), fc)
+    except Exception:
+        ctx.restore(snap)  # nothing reached the device: keep host and device counters in step
+        raise
     cuda_ext.note_launch()
     return out, lse
 
@@ -294,6 +387,12 @@ def reduce_tasks(plan: CPPlan, ctx: PeerContext, device):
     key = ("reduce", device.index)
     cache = attn_cuda._cache(plan)
     if key in cache:
+        return cache[key]
+    if is_dynamic(plan):
+        # who contributes which rows is only known on the device: fixed row blocks, masks computed by the kernel
+        rows, blk = plan.kv_rows, 512
+        cache[key] = torch.tensor([[r0, min(blk, rows - r0), 0, 0] for r0 in range(0, rows, blk)],
+                                  dtype=torch.int32).to(device)
         return cache[key]
     needs = needs_matrix(plan, ctx.group)
     me, world, rows = plan.rank, plan.world, plan.kv_rows
@@ -336,17 +435,23 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
         items, qsegs, per_owner = attn_cuda.bwd_tables_fused(plan, offsets, q.device, flags)
     delta = attn_cuda.compute_delta(out, dout)
     dq = attn_cuda.dq_workspace.acquire(q)  # zeroed fp32 accumulator, re-zeroed by dq_finalize
-    fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hkv)
-    me, esize = plan.rank, k.element_size()
-    fc.dk_ptrs = [p + me * ctx.inbox_slot_stride * esize for p in ctx.inbox.ptrs]
-    fc.dv_ptrs = [p + (me * ctx.inbox_slot_stride + ctx.inbox_kv_stride) * esize for p in ctx.inbox.ptrs]
-    for o in range(plan.world):
-        ctx.dkv_cum[o] = (ctx.dkv_cum[o] + per_owner[o] * hkv) & MASK32
-    fc.dkv_targets = list(ctx.dkv_cum)
-    fc.dkv_wait_epoch = ctx.last_bwd_epoch
-    launch = C.attn_bwd_fused_window if window else C.attn_bwd_fused
-    launch(attn_cuda._rows3(q), attn_cuda._rows3(dout), k, v, dq, items, qsegs, lse.contiguous(), delta,
-           q.shape[0], float(scale), fc)
+    dyn = needs_gathered(plan, ctx, q.device) if is_dynamic(plan) else None
+    snap = ctx.snapshot()
+    try:
+        fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hkv, dyn)
+        me, esize = plan.rank, k.element_size()
+        fc.dk_ptrs = [p + me * ctx.inbox_slot_stride * esize for p in ctx.inbox.ptrs]
+        fc.dv_ptrs = [p + (me * ctx.inbox_slot_stride + ctx.inbox_kv_stride) * esize for p in ctx.inbox.ptrs]
+        for o in range(plan.world):
+            ctx.dkv_cum[o] = (ctx.dkv_cum[o] + per_owner[o] * hkv) & MASK32
+        fc.dkv_targets = list(ctx.dkv_cum)
+        fc.dkv_wait_epoch = ctx.last_bwd_epoch
+        launch = C.attn_bwd_fused_window if window else C.attn_bwd_fused
+        launch(attn_cuda._rows3(q), attn_cuda._rows3(dout), k, v, dq, items, qsegs, lse.contiguous(), delta,
+               q.shape[0], float(scale), fc)
+    except Exception:
+        ctx.restore(snap)  # nothing reached the device: keep host and device counters in step
+        raise
     cuda_ext.note_launch()
     # owner-side reduction of the inbox (waits for the peers' "gradients landed" epochs on the device)
     tasks = reduce_tasks(plan, ctx, q.device)

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-2 multi-GPU validation (N = all visible GPUs): fused tests (model-dtype dK/dV inbox, device-side needs
+# exchange for llama3, window kernels), per-phase breakdown, headline bench with the sampled oracle check.
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l)
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 1200 python -m pytest tests/test_gpu_multi.py -m gpu -q -x --timeout 900 > gpurun_out/pytest_multi_$N.log 2>&1; echo "multi tests exit $?"; tail -6 gpurun_out/pytest_multi_$N.log
+SWEEP=24 timeout 600 $TR --master-port 29542 benchmark/multi_breakdown.py > gpurun_out/breakdown_r2_$N.log 2>&1; grep -E "^t[0-9]" gpurun_out/breakdown_r2_$N.log | cut -c1-140
+timeout 600 $TR --master-port 29545 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_r2_ours_$N.log 2>&1; grep '"metric"' gpurun_out/bench_r2_ours_$N.log | cut -c1-1800
+if [ "${REF:-0}" = "1" ]; then
+  timeout 600 $TR --master-port 29546 bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_r2_reference_$N.log 2>&1; grep '"metric"' gpurun_out/bench_r2_reference_$N.log | cut -c1-700
+fi
+if [ "${CONFIGS:-0}" = "1" ]; then
+  for impl in ours reference; do
+    timeout 900 $TR --master-port 29543 benchmark/bench_configs.py --impl $impl > gpurun_out/bench_configs_r2_${impl}_$N.jsonl 2> gpurun_out/bench_configs_r2_${impl}_$N.err
+    grep '^{' gpurun_out/bench_configs_r2_${impl}_$N.jsonl | cut -c1-330
+  done
+fi

@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+# a protocol bug in a fused multi-GPU test must fail fast (device trap), not sit out the production limit of 600 s
+os.environ.setdefault("RFA_B200_PEER_TIMEOUT_S", "30")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,4 +1,5 @@
 """Spawn a small torch.distributed world inside a test (gloo on CPU, nccl on GPUs)."""
+import datetime
 import os
 import tempfile
 import traceback
@@ -13,7 +14,9 @@ def _worker(rank, world, backend, init_file, fn, args, err_q):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if backend == "nccl":
             torch.cuda.set_device(rank)
-        dist.init_process_group(backend, init_method=f"file://{init_file}", rank=rank, world_size=world)
+        # a rank that fails an assertion leaves its peers inside a collective: bound that wait (default: 10 min)
+        dist.init_process_group(backend, init_method=f"file://{init_file}", rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=120))
         fn(rank, world, *args)
         dist.barrier()
         dist.destroy_process_group()

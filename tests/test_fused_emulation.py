@@ -53,10 +53,28 @@ def _replay(plans, world, L, hq, hkv, lq, lk, lv, ldo, ref_out, ref_lse, ref_dq,
     stage_k = [torch.full((world * L, hkv, D), float("nan")) for _ in range(world)]
     stage_v = [torch.full((world * L, hkv, D), float("nan")) for _ in range(world)]
     region = world * L * row_bytes
+    dynamic = symm.is_dynamic(plans[0])
+    # llama3-style plans: every rank only knows its own needs; the all-gather of the local tables is what
+    # symm.needs_gathered does on the device, and the push / reduce roles derive their work from it
+    needs_all = torch.stack([symm.local_needs_table(p) for p in plans]).tolist() if dynamic else None
     for me, p in enumerate(plans):
-        tasks, per_dst = symm.push_tasks(p, _Ctx(), row_bytes, torch.device("cpu"))
-        assert per_dst[me] == 0
-        for src_row, dst_off, packed, which in tasks.tolist():
+        if dynamic:
+            assert symm.dynamic_ok(p)
+            chunk = symm.push_chunk_rows(row_bytes)
+            chunks = -(-L // chunk)
+            n_tasks = (world - 1) * 2 * symm.NEED_RANGES * chunks
+            tasks = []
+            for ti in range(n_tasks):
+                src_row, dst_off, rows, dst, which = symm.dynamic_push_task(needs_all, me, world, ti, chunk, chunks, L,
+                                                                           row_bytes, region)
+                assert dst != me
+                if rows:
+                    tasks.append([src_row, dst_off, rows | (dst << 32), which])
+        else:
+            t, per_dst = symm.push_tasks(p, _Ctx(), row_bytes, torch.device("cpu"))
+            assert per_dst[me] == 0
+            tasks = t.tolist()
+        for src_row, dst_off, packed, which in tasks:
             rows, dst = packed & 0xFFFFFFFF, packed >> 32
             assert dst_off % row_bytes == 0
             dst_row = (dst_off - which * region) // row_bytes
@@ -107,6 +125,9 @@ def _replay(plans, world, L, hq, hkv, lq, lk, lv, ldo, ref_out, ref_lse, ref_dq,
     for me, p in enumerate(plans):
         tasks = symm.reduce_tasks(p, _Ctx(), torch.device("cpu")).tolist()
         dk, dv = torch.zeros(L, hkv, D), torch.zeros(L, hkv, D)
+        if dynamic:  # fixed row blocks; the kernel computes the contributing ranks per row from the needs table
+            tasks = [[r, 1, symm.dynamic_row_mask(needs_all, me, world, r), 0]
+                     for row0, rows, _m, _p in tasks for r in range(row0, row0 + rows)]
         for row0, rows, mask, _pad in tasks:
             for s in range(world):
                 if (mask >> s) & 1:
@@ -139,10 +160,11 @@ def test_fused_tables_end_to_end(scheme, window):
 
 @pytest.mark.parametrize("window", [(-1, -1), (200, 0)])
 def test_fused_tables_llama3(window):
-    """llama3 layout (contiguous split of packed documents): peers' plans come from the global cu_seqlens that
-    prepare() attaches, exactly as parallel/api.py derives them at run time."""
+    """llama3 layout (contiguous split of packed documents): every rank's plan is built from its OWN prepare()
+    outputs only; what the peers need of a shard comes from their plans (on hardware: the device-side needs
+    exchange, parallel/symm.py:needs_gathered)."""
     from ring_flash_attn_b200.ops.dense import varlen_attention_oracle
-    from ring_flash_attn_b200.parallel import api
+    from ring_flash_attn_b200.parallel import api, ops
 
     world, L, hq, hkv = 4, 256, 4, 2
     S = world * L
@@ -152,7 +174,11 @@ def test_fused_tables_llama3(window):
     rq, rk, rv = (t.clone().requires_grad_(True) for t in (q, k, v))
     ref, ref_lse = varlen_attention_oracle(rq, rk, rv, torch.tensor(cu), True, window_size=window)
     ref.backward(dout)
-    plans = [api._llama3_peer_plan(cu, True, r, world, L, window) for r in range(world)]
+    plans = []
+    for r in range(world):
+        cq, ck, _mq, _mk, ks = api.llama3_flash_attn_prepare_cu_seqlens(torch.tensor(cu, dtype=torch.int32), True, r,
+                                                                       world)
+        plans.append(ops.llama3_plan(r, world, L, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), True, window))
     sh = lambda x, r: layouts.shard_llama3(x, r, world)  # noqa: E731
     R = range(world)
     _replay(plans, world, L, hq, hkv, [sh(q, r) for r in R], [sh(k, r) for r in R], [sh(v, r) for r in R],
@@ -164,7 +190,7 @@ def test_fused_tables_llama3(window):
 @pytest.mark.parametrize("window", [(-1, -1), (200, 0)])
 def test_fused_tables_zigzag_llama3(window):
     from ring_flash_attn_b200.ops.dense import varlen_attention_oracle
-    from ring_flash_attn_b200.parallel import api
+    from ring_flash_attn_b200.parallel import ops
 
     world, L, hq, hkv = 4, 256, 4, 2
     S = world * L
@@ -174,7 +200,7 @@ def test_fused_tables_zigzag_llama3(window):
     rq, rk, rv = (t.clone().requires_grad_(True) for t in (q, k, v))
     ref, ref_lse = varlen_attention_oracle(rq, rk, rv, torch.tensor(cu), True, window_size=window)
     ref.backward(dout)
-    plans = [api._zigzag_llama3_plan(r, world, cu, True, window) for r in range(world)]
+    plans = [ops.zigzag_llama3_plan(r, world, cu, True, window) for r in range(world)]
     sh = lambda x, r: layouts.shard_zigzag_llama3(x, r, world)  # noqa: E731
     R = range(world)
     _replay(plans, world, L, hq, hkv, [sh(q, r) for r in R], [sh(k, r) for r in R], [sh(v, r) for r in R],

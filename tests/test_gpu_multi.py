@@ -253,3 +253,41 @@ def test_fused_subgroups_4gpu():
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs")
     run_distributed(_subgroup_fused_case, 4, backend="nccl")
+
+
+def _compiled_case(rank, world):
+    """Every scheme once under torch.compile(fullgraph=True) on the fused path, against eager."""
+    os.environ["RFA_B200_DISABLE_P2P"] = "0"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(3)
+    s_l, h = 1024, 4
+    qkv = torch.randn(1, s_l, 3, h, 128, device=dev).to(torch.bfloat16)
+    dout = torch.randn(1, s_l, h, 128, device=dev).to(torch.bfloat16)
+    cu_local = torch.tensor([0, 256, s_l], dtype=torch.int32)
+    cu_global = torch.tensor([0, 300 * world, s_l * world], dtype=torch.int32)
+    cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu_global, True, rank, world)
+
+    def f(x):
+        a = rfa.zigzag_ring_flash_attn_qkvpacked_func(x, causal=True)
+        b = rfa.stripe_flash_attn_qkvpacked_func(x, causal=True)
+        c = rfa.zigzag_ring_flash_attn_varlen_qkvpacked_func(x[0], cu_local, 768, causal=True)
+        d = rfa.llama3_flash_attn_varlen_qkvpacked_func(x[0], cq, ck, mq, mk, heads_k_stride=1, local_k_slice=ks,
+                                                        causal=True)
+        return a + b + (c + d).unsqueeze(0)
+
+    x = qkv.detach().requires_grad_(True)
+    ref = f(x)
+    ref.backward(dout)
+    g_ref = x.grad.clone()
+    y = qkv.detach().requires_grad_(True)
+    out = torch.compile(f, backend="aot_eager", fullgraph=True)(y)
+    out.backward(dout)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.float(), ref.float(), atol=1e-2, rtol=1e-2)
+    _close(y.grad, g_ref, "compiled grad", rel=2e-2, abs_=1e-2)
+
+
+def test_compiled_schemes_2gpu():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_compiled_case, 2, backend="nccl")

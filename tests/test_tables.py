@@ -98,21 +98,31 @@ def test_fused_tables_push_and_reduce_are_consistent(scheme):
         assert sum(per_owner) == items.shape[0]
 
 
-def test_llama3_same_local_slice_different_global_layouts_do_not_share_caches():
-    """Two global packings can give a rank the same local description; its peers' needs still differ."""
+def test_llama3_needs_are_exchanged_not_derived():
+    """Two global packings can give a rank the same local description while its peers' needs differ: llama3 plans
+    therefore carry no ``peer`` function and the fused path gathers every rank's needs table on the device at each
+    launch (parallel/symm.py:needs_gathered).  The local table is exactly the row ranges the plan reads."""
+    from ring_flash_attn_b200.parallel import ops
+
     world, T = 8, 64
     a = torch.tensor([0, 8 * T], dtype=torch.int32)
     b = torch.tensor([0, 5 * T, 8 * T], dtype=torch.int32)
     pa = api.llama3_flash_attn_prepare_cu_seqlens(a, True, 0, world)
     pb = api.llama3_flash_attn_prepare_cu_seqlens(b, True, 0, world)
     assert pa[0].tolist() == pb[0].tolist() and pa[1].tolist() == pb[1].tolist()  # identical for rank 0
-    assert pa[0]._rfa_llama3[0] != pb[0]._rfa_llama3[0]
-    plan_a = api._llama3_plan(0, world, T, tuple(pa[0].tolist()), tuple(pa[1].tolist()), 0, True, pa[0]._rfa_llama3[0])
-    plan_b = api._llama3_plan(0, world, T, tuple(pb[0].tolist()), tuple(pb[1].tolist()), 0, True, pb[0]._rfa_llama3[0])
-    assert plan_a is not plan_b
-    peers_a = api._llama3_peer_plan(pa[0]._rfa_llama3[0], True, 6, world, T)
-    peers_b = api._llama3_peer_plan(pb[0]._rfa_llama3[0], True, 6, world, T)
-    assert symm._ranges(peers_a, 0) and not symm._ranges(peers_b, 0)  # rank 6 needs rank 0's keys only in layout a
+    plans = {}
+    for name, cu in (("a", a), ("b", b)):
+        cq, ck, _mq, _mk, ks = api.llama3_flash_attn_prepare_cu_seqlens(cu, True, 6, world)
+        plans[name] = ops.llama3_plan(6, world, T, tuple(cq.tolist()), tuple(ck.tolist()), int(ks.start), True)
+    for p in plans.values():
+        assert symm.is_dynamic(p) and symm.dynamic_ok(p) and not hasattr(p, "peer")
+    assert symm._ranges(plans["a"], 0) and not symm._ranges(plans["b"], 0)  # rank 6 needs rank 0's keys only in a
+
+    class Ctx:
+        group = None
+
+    tasks = symm.reduce_tasks(plans["a"], Ctx(), torch.device("cpu")).tolist()
+    assert tasks[0][0] == 0 and sum(t[1] for t in tasks) == T  # fixed row blocks; masks are computed on the device
 
 
 # ----------------------------------------------------------------------------------------------
