@@ -40,17 +40,22 @@ namespace bwd {
   } while (0)
 #endif
 
-constexpr int kD = 128;
 constexpr int kTileK = 128;  // keys per CTA
 constexpr int kTileQ = 64;   // queries per inner iteration
 constexpr int kStages = 3;   // Q/dO ring
 constexpr int kThreads = 512;
-constexpr int kKVBytes = kTileK * kD * 2;          // 32 KB each for K and V
-constexpr int kQBytes = kTileQ * kD * 2;           // 16 KB each for Q and dO
-constexpr int kQHalf = kQBytes / 2;                // 64-wide swizzled sub-tile of a 64-row tile (8 KB)
-constexpr int kKVHalf = kKVBytes / 2;              // 16 KB
+constexpr int kQHalf = kTileQ * 128;               // 64-wide swizzled sub-tile of a 64-row tile (8 KB)
+constexpr int kKVHalf = kTileK * 128;              // 64-wide swizzled sub-tile of a 128-row tile (16 KB)
 constexpr int kDSBytes = kTileK * kTileQ * 2;      // 16 KB
-constexpr int kDQBytes = kTileQ * kD * 4;          // 32 KB fp32 staging
+// Head dim kD (64 or 128) is a template parameter: tiles are kD / 64 sub-tiles wide, dK / dV take kD columns.
+template <int kD>
+struct Geo {
+  static constexpr int kKVBytes = kTileK * kD * 2;  // K, V tile: 32 KB at kD = 128
+  static constexpr int kQBytes = kTileQ * kD * 2;   // Q, dO tile: 16 KB
+  static constexpr int kDQBytes = kTileQ * kD * 4;  // fp32 dQ staging: 32 KB
+  static constexpr int kSmemBytes = 2 * kKVBytes + kStages * 2 * kQBytes + kDSBytes + kDQBytes +
+                                    kStages * 2 * kTileQ * 4 /*stats*/ + 1024 /*barriers*/ + 1024 /*slack*/;
+};
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 192, kColDV = 256, kColDK = 384;
 
@@ -72,8 +77,6 @@ struct Barriers {
 };
 
 constexpr int kStatBytes = kStages * 2 * kTileQ * 4;  // lse / delta ring, same slots as Q/dO
-constexpr int kSmemBytes =
-    2 * kKVBytes + kStages * 2 * kQBytes + kDSBytes + kDQBytes + kStatBytes + 1024 /*barriers*/ + 1024 /*slack*/;
 
 // Query tiles of one segment that can see this key tile.
 struct QGeom {
@@ -93,7 +96,7 @@ __device__ __forceinline__ QGeom q_geom(const BwdQSegment& s) {
   return g;
 }
 
-template <typename T, bool kWindow>
+template <typename T, bool kWindow, int kD>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -109,6 +112,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     return;
   }
+  static_assert(kD == 64 || kD == 128, "head dim 64 or 128");
+  constexpr int kKVBytes = Geo<kD>::kKVBytes, kQBytes = Geo<kD>::kQBytes, kDQBytes = Geo<kD>::kDQBytes;
+  constexpr int kSubTiles = kD / 64;
   const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,9 +128,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kv_head = cta / p.n_items;
+  // CTA -> (key tile, kv head).  One GPU: head-major, so that concurrently running CTAs re-read the Q / dO of ONE
+  // head out of L2 (at S = 32K all heads together do not fit).  Fused multi-GPU launches: tile-major - the table
+  // is sorted by ring step (local keys first, then the sources in the order their K/V arrives), and with head-major
+  // numbering the tiles of the LAST source of head 0 would be scheduled, and sit waiting for their data, before any
+  // tile of head 1 that could already run.
+  const int kv_head = p.item_major ? cta % p.hkv : cta / p.n_items;
   const int group = p.hq / p.hkv;
-  const BwdItem it = p.items[cta % p.n_items];
+  const BwdItem it = p.items[p.item_major ? cta / p.hkv : cta % p.n_items];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -182,10 +193,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const CUtensorMap* mk = staged ? &tm_ks : &tm_k;
         const CUtensorMap* mv = staged ? &tm_vs : &tm_v;
         mbar_arrive_expect_tx(&bars->kv_full, 2 * kKVBytes);
-        tma_load_3d(smem_k, mk, &bars->kv_full, 0, kv_head, it.kv_row0);
-        tma_load_3d(smem_k + kKVHalf, mk, &bars->kv_full, 64, kv_head, it.kv_row0);
-        tma_load_3d(smem_v, mv, &bars->kv_full, 0, kv_head, it.kv_row0);
-        tma_load_3d(smem_v + kKVHalf, mv, &bars->kv_full, 64, kv_head, it.kv_row0);
+#pragma unroll
+        for (int h = 0; h < kSubTiles; ++h) {
+          tma_load_3d(smem_k + h * kKVHalf, mk, &bars->kv_full, 64 * h, kv_head, it.kv_row0);
+          tma_load_3d(smem_v + h * kKVHalf, mv, &bars->kv_full, 64 * h, kv_head, it.kv_row0);
+        }
         uint32_t slot = 0, phase = 0;
         for (int gq = 0; gq < group; ++gq) {
           const int head = kv_head * group + gq;
@@ -197,10 +209,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               uint8_t* dq_ = smem_qdo + slot * 2 * kQBytes;
               uint8_t* ddo = dq_ + kQBytes;
               mbar_arrive_expect_tx(&bars->qdo_full[slot], 2 * kQBytes);
-              tma_load_3d(dq_, &tm_q, &bars->qdo_full[slot], 0, head, row);
-              tma_load_3d(dq_ + kQHalf, &tm_q, &bars->qdo_full[slot], 64, head, row);
-              tma_load_3d(ddo, &tm_do, &bars->qdo_full[slot], 0, head, row);
-              tma_load_3d(ddo + kQHalf, &tm_do, &bars->qdo_full[slot], 64, head, row);
+#pragma unroll
+              for (int h = 0; h < kSubTiles; ++h) {
+                tma_load_3d(dq_ + h * kQHalf, &tm_q, &bars->qdo_full[slot], 64 * h, head, row);
+                tma_load_3d(ddo + h * kQHalf, &tm_do, &bars->qdo_full[slot], 64 * h, head, row);
+              }
               if (++slot == kStages) {
                 slot = 0;
                 phase ^= 1;
@@ -217,7 +230,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         constexpr uint32_t fmt = Pack2<T>::kFmt;
         constexpr uint32_t idesc_st = umma_idesc_f16(fmt, kTileK, kTileQ, 0, 0);  // S^T, dP^T
         constexpr uint32_t idesc_dv = umma_idesc_f16(fmt, kTileK, kD, 0, 1);      // dV (A tmem), dK (A smem)
-        constexpr uint32_t idesc_dq = umma_idesc_f16(fmt, kD, kTileQ, 1, 1);      // dQ^T
+        // dQ^T has M = head dims.  For kD = 64 the instruction still runs with M = 128: the upper 64 "dims" of the
+        // MN-major A operand fall into whatever follows the K tile in shared memory (the V tile) and produce
+        // garbage accumulator LANES 64..127, which the drain warps never read - rows of D are independent, and
+        // it avoids the different tensor-memory layout of M = 64 accumulators.
+        constexpr uint32_t idesc_dq = umma_idesc_f16(fmt, 128, kTileQ, 1, 1);     // dQ^T
         const uint32_t k_base = smem_u32(smem_k), v_base = smem_u32(smem_v);
         const uint32_t qdo_base = smem_u32(smem_qdo), ds_base = smem_u32(smem_ds);
 
@@ -511,12 +528,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto store_rows = [&](auto tag) {
       using O = decltype(tag);
       constexpr int kRowBytes = kD * static_cast<int>(sizeof(O));
+      constexpr int kKVBytes = Geo<kD>::kKVBytes, kQBytes = Geo<kD>::kQBytes;
       constexpr int kPitch = kRowBytes + 16;
       static_assert(2 * kTileK * kPitch <= 2 * kKVBytes + kStages * 2 * kQBytes, "staging must fit in K|V|Q/dO");
       uint8_t* mine = smem_k + half * (kTileK * kPitch) + key * kPitch;
       const uint32_t col = tmem + (half == 0 ? kColDK : kColDV) + lane_addr;
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = 0; c < kD; c += 32) {
         uint32_t r[32];
         if (total_tiles > 0) {
           tmem_ld32(col + c, r);
@@ -590,8 +608,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           // the previous tile's reduce must have finished reading the staging buffer
           if (wg_tid == 0) tma_store_wait_read<0>();
           named_bar_sync(4, 128);
+          if (wg_tid < kD) {  // (kD = 64: lanes 64..127 of the M = 128 accumulator are not dQ)
 #pragma unroll
-          for (int q = 0; q < kTileQ; ++q) smem_dq[q * kD + wg_tid] = __uint_as_float(r[q]);
+            for (int q = 0; q < kTileQ; ++q) smem_dq[q * kD + wg_tid] = __uint_as_float(r[q]);
+          }
           fence_proxy_async_smem();
           named_bar_sync(4, 128);
           if (wg_tid == 0) {
@@ -615,18 +635,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 template <typename T>
 __global__ void bwd_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
                                  int rows, int hq, int lse_S, int64_t o_rs, int64_t o_hs, int64_t do_rs,
-                                 int64_t do_hs) {
+                                 int64_t do_hs, int head_dim) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= rows * hq) return;
   const int row = gw / hq, head = gw % hq;
-  const uint2 a = *reinterpret_cast<const uint2*>(out + row * o_rs + head * o_hs + lane * 4);
-  const uint2 b = *reinterpret_cast<const uint2*>(dout + row * do_rs + head * do_hs + lane * 4);
-  const T* pa = reinterpret_cast<const T*>(&a);
-  const T* pb = reinterpret_cast<const T*>(&b);
   float s = 0.f;
+  if (lane * 4 < head_dim) {  // 4 elements per lane: 32 lanes cover head_dim 128, 16 lanes head_dim 64
+    const uint2 a = *reinterpret_cast<const uint2*>(out + row * o_rs + head * o_hs + lane * 4);
+    const uint2 b = *reinterpret_cast<const uint2*>(dout + row * do_rs + head * do_hs + lane * 4);
+    const T* pa = reinterpret_cast<const T*>(&a);
+    const T* pb = reinterpret_cast<const T*>(&b);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) s += static_cast<float>(pa[i]) * static_cast<float>(pb[i]);
+    for (int i = 0; i < 4; ++i) s += static_cast<float>(pa[i]) * static_cast<float>(pb[i]);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) {
@@ -638,7 +660,7 @@ __global__ void bwd_delta_kernel(const T* __restrict__ out, const T* __restrict_
 }  // namespace bwd
 
 const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const TensorView& dout, float* delta, int lse_S,
-                                  cudaStream_t stream) {
+                                  int head_dim, cudaStream_t stream) {
   const int rows = static_cast<int>(out.rows), hq = out.heads;
   const long long warps = static_cast<long long>(rows) * hq;
   if (warps == 0) return nullptr;
@@ -647,11 +669,11 @@ const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const Tensor
   if (dtype == kDtypeBF16) {
     bwd::bwd_delta_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(out.ptr), static_cast<const __nv_bfloat16*>(dout.ptr), delta, rows, hq, lse_S,
-        out.row_stride, out.head_stride, dout.row_stride, dout.head_stride);
+        out.row_stride, out.head_stride, dout.row_stride, dout.head_stride, head_dim);
   } else {
     bwd::bwd_delta_kernel<__half><<<blocks, threads, 0, stream>>>(
         static_cast<const __half*>(out.ptr), static_cast<const __half*>(dout.ptr), delta, rows, hq, lse_S,
-        out.row_stride, out.head_stride, dout.row_stride, dout.head_stride);
+        out.row_stride, out.head_stride, dout.row_stride, dout.head_stride, head_dim);
   }
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
@@ -664,27 +686,34 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
   if (n_blocks <= 0) return nullptr;
   if (p.sig.world > 0) set_peer_timeout_from_env();
   CUtensorMap tq, tdo, tk, tv, tks, tvs, tdq;
-  if (const char* e = make_tensor_map(&tq, q, 2, bwd::kTileQ, bwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tdo, dout, 2, bwd::kTileQ, bwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tk, k, 2, bwd::kTileK, bwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tv, v, 2, bwd::kTileK, bwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tks, k_stage, 2, bwd::kTileK, bwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tvs, v_stage, 2, bwd::kTileK, bwd::kD)) return e;
-  if (const char* e = make_plain_tensor_map(&tdq, dq_accum, 4, bwd::kTileQ, bwd::kD)) return e;
+  const int d = p.head_dim;
+  if (d != 64 && d != 128) return "the sm_100a backward is instantiated for head_dim 64 and 128";
+  if (const char* e = make_tensor_map(&tq, q, 2, bwd::kTileQ, d)) return e;
+  if (const char* e = make_tensor_map(&tdo, dout, 2, bwd::kTileQ, d)) return e;
+  if (const char* e = make_tensor_map(&tk, k, 2, bwd::kTileK, d)) return e;
+  if (const char* e = make_tensor_map(&tv, v, 2, bwd::kTileK, d)) return e;
+  if (const char* e = make_tensor_map(&tks, k_stage, 2, bwd::kTileK, d)) return e;
+  if (const char* e = make_tensor_map(&tvs, v_stage, 2, bwd::kTileK, d)) return e;
+  if (const char* e = make_plain_tensor_map(&tdq, dq_accum, 4, bwd::kTileQ, d)) return e;
   dim3 grid(n_blocks, 1, 1), block(bwd::kThreads, 1, 1);
   cudaError_t err;
   err = cudaSuccess;
-  auto launch = [&](auto kern) {
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
-    if (err == cudaSuccess) kern<<<grid, block, bwd::kSmemBytes, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
+  auto launch = [&](auto kern, int smem) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err == cudaSuccess) kern<<<grid, block, smem, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   };
-  if (dtype == kDtypeBF16) {
-    if (p.window) launch(bwd::attn_bwd_kernel<__nv_bfloat16, true>);
-    else launch(bwd::attn_bwd_kernel<__nv_bfloat16, false>);
-  } else {
-    if (p.window) launch(bwd::attn_bwd_kernel<__half, true>);
-    else launch(bwd::attn_bwd_kernel<__half, false>);
-  }
+  auto pick = [&](auto tag) {
+    using T = decltype(tag);
+    if (d == 128) {
+      if (p.window) launch(bwd::attn_bwd_kernel<T, true, 128>, bwd::Geo<128>::kSmemBytes);
+      else launch(bwd::attn_bwd_kernel<T, false, 128>, bwd::Geo<128>::kSmemBytes);
+    } else {
+      if (p.window) launch(bwd::attn_bwd_kernel<T, true, 64>, bwd::Geo<64>::kSmemBytes);
+      else launch(bwd::attn_bwd_kernel<T, false, 64>, bwd::Geo<64>::kSmemBytes);
+    }
+  };
+  if (dtype == kDtypeBF16) pick(__nv_bfloat16{});
+  else pick(__half{});
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();
   return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

@@ -26,7 +26,7 @@ struct alignas(16) KVSegment {
   int flag;  // fused multi-GPU mode: index of the "rows have landed" flag to wait on, -1 = local data
 };
 
-// Tensor view handed to the launchers: (rows, heads, 128) with element strides.
+// Tensor view handed to the launchers: (rows, heads, head_dim) with element strides.
 struct TensorView {
   void* ptr;
   int64_t rows;
@@ -146,6 +146,7 @@ struct FwdParams {
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;
   int hq, hkv;
+  int head_dim;      // 64 or 128 (selects the kernel instantiation)
   float scale;       // softmax scale
   float scale_log2;  // scale * log2(e)
   const uint32_t* ready_flags;  // fused mode only: this rank's signal pad (kPadKvReady + src)
@@ -185,11 +186,13 @@ struct BwdParams {
   int dkv_fp32;        // 1: dk / dv are fp32 (fallback transports accumulate ring steps), 0: model dtype
   int lse_S;
   int hq, hkv;
+  int head_dim;        // 64 or 128 (selects the kernel instantiation)
   float scale, scale_log2;
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
   int n_items;
   int window;  // != 0: BwdQSegment::lo is meaningful (selects the kernel variant that masks the lower band edge)
+  int item_major;  // CTA numbering: 0 = head-major (one GPU), 1 = key-tile-major (fused launches, table in ring order)
   unsigned long long* trace;  // RFA_TRACE builds only
   PushParams push;
   SignalParams sig;
@@ -217,7 +220,7 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
                             cudaStream_t stream);
 
 const char* attn_bwd_delta_launch(int dtype, const TensorView& out, const TensorView& dout, float* delta, int lse_S,
-                                  cudaStream_t stream);
+                                  int head_dim, cudaStream_t stream);
 const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& dout, const TensorView& k,
                             const TensorView& v, const TensorView& k_stage, const TensorView& v_stage,
                             const TensorView& dq_accum, const BwdParams& p, cudaStream_t stream);

@@ -28,8 +28,6 @@
 
 namespace rfa {
 
-constexpr int kDefaultPolyOf4 = 0;  // measured on B200: see profiles/ (MUFU-only is the fastest so far)
-
 namespace fwd {
 
 #ifdef RFA_TRACE
@@ -44,12 +42,21 @@ namespace fwd {
   } while (0)
 #endif
 
-constexpr int kD = 128;             // head dim
 constexpr int kTile = 128;          // rows per MMA tile (queries and keys)
 constexpr int kStages = 4;          // K/V ring slots
-constexpr int kTileBytes = kTile * kD * 2;  // 32 KB
-constexpr int kHalfBytes = kTileBytes / 2;  // one 64-element-wide swizzled sub-tile
+constexpr int kHalfBytes = kTile * 128;  // one 64-element-wide (128-byte) swizzled sub-tile: 16 KB
 constexpr int kThreads = 384;
+// Head dim kD is a template parameter (64 or 128): a tile is kD / 64 sub-tiles of 128 rows x 128 bytes, the output
+// accumulator kD tensor-memory columns.  (The reference inherits its head sizes from flash-attn; smaller sizes are
+// zero-padded to the next supported one in parallel/api.py.)
+template <int kD>
+constexpr int tile_bytes() {
+  return kTile * kD * 2;
+}
+template <int kD>
+constexpr int smem_bytes() {
+  return 2 * tile_bytes<kD>() + kStages * tile_bytes<kD>() + 1024 /*barriers*/ + 1024 /*align slack*/;
+}
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; P stays below 2^8
@@ -65,8 +72,6 @@ struct Barriers {
   uint32_t pad;
 };
 
-constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
-
 // Element traits.  Fp8E4M3 is the tag of the experimental fp8 forward (RFA_B200_FP8_KERNEL=1): q / k / v are e4m3
 // bytes, a tile is ONE 128-byte swizzle span per row (16 KB, loaded into the same 32 KB slots), both GEMMs are
 // kind::f8f6f4 with K = 32 per instruction, P is written back to tensor memory as e4m3 (four per column) and the
@@ -76,14 +81,14 @@ struct Fp8E4M3 {};
 template <typename T>
 struct Elem {
   static constexpr bool kFp8 = false;
-  static constexpr uint32_t kTxBytes = kTileBytes;
+  static constexpr uint32_t kBytes = 2;
   static constexpr uint32_t kFmt = Pack2<T>::kFmt;
   using Out = T;
 };
 template <>
 struct Elem<Fp8E4M3> {
   static constexpr bool kFp8 = true;
-  static constexpr uint32_t kTxBytes = kTile * kD;
+  static constexpr uint32_t kBytes = 1;
   static constexpr uint32_t kFmt = 0;  // e4m3
   using Out = __nv_bfloat16;
 };
@@ -126,8 +131,7 @@ __device__ __forceinline__ bool tile_needs_lower_mask(int lo, const WorkItem& it
   return last_row + lo > static_cast<long long>(jj) * kTile;
 }
 
-// kPolyOf4: of every 4 element pairs, this many use the polynomial exp2 (0 = MUFU only)
-template <typename T, int kPolyOf4, bool kWindow>
+template <typename T, bool kWindow, int kD>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_ks,
@@ -144,6 +148,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     return;
   }
   using E = Elem<T>;
+  static_assert(kD == 64 || kD == 128, "head dim 64 or 128");
+  static_assert(!E::kFp8 || kD == 128, "the fp8 forward is instantiated for head dim 128 only");
+  constexpr int kTileBytes = tile_bytes<kD>();   // smem slot of one tile (fp8 tiles use the first half of it)
+  constexpr int kSubTiles = E::kFp8 ? 1 : kD / 64;  // 128-byte spans per row
+  constexpr uint32_t kTxBytes = kTile * kD * E::kBytes;
   const int cta = static_cast<int>(blockIdx.x) - p.push.n_ctas;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -190,14 +199,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
    if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->q_full[0], E::kTxBytes);
-      tma_load_3d(smem_q, &tm_q, &bars->q_full[0], 0, head, it.q_row0);
-      if constexpr (!E::kFp8) tma_load_3d(smem_q + kHalfBytes, &tm_q, &bars->q_full[0], 64, head, it.q_row0);
+      mbar_arrive_expect_tx(&bars->q_full[0], kTxBytes);
+#pragma unroll
+      for (int h = 0; h < kSubTiles; ++h)
+        tma_load_3d(smem_q + h * kHalfBytes, &tm_q, &bars->q_full[0], 64 * h, head, it.q_row0);
       if (has_t1) {
-        mbar_arrive_expect_tx(&bars->q_full[1], E::kTxBytes);
-        tma_load_3d(smem_q + kTileBytes, &tm_q, &bars->q_full[1], 0, head, it.q_row0 + kTile);
-        if constexpr (!E::kFp8)
-          tma_load_3d(smem_q + kTileBytes + kHalfBytes, &tm_q, &bars->q_full[1], 64, head, it.q_row0 + kTile);
+        mbar_arrive_expect_tx(&bars->q_full[1], kTxBytes);
+#pragma unroll
+        for (int h = 0; h < kSubTiles; ++h)
+          tma_load_3d(smem_q + kTileBytes + h * kHalfBytes, &tm_q, &bars->q_full[1], 64 * h, head, it.q_row0 + kTile);
       }
       uint32_t slot = 0, phase = 0;
       for (int si = 0; si < it.seg_count; ++si) {
@@ -214,9 +224,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(&bars->kv_empty[slot], phase ^ 1);
             uint8_t* dst = smem_kv + slot * kTileBytes;
             const CUtensorMap* tm = staged ? (kv == 0 ? &tm_ks : &tm_vs) : (kv == 0 ? &tm_k : &tm_v);
-            mbar_arrive_expect_tx(&bars->kv_full[slot], E::kTxBytes);
-            tma_load_3d(dst, tm, &bars->kv_full[slot], 0, kv_head, row);
-            if constexpr (!E::kFp8) tma_load_3d(dst + kHalfBytes, tm, &bars->kv_full[slot], 64, kv_head, row);
+            mbar_arrive_expect_tx(&bars->kv_full[slot], kTxBytes);
+#pragma unroll
+            for (int h = 0; h < kSubTiles; ++h)
+              tma_load_3d(dst + h * kHalfBytes, tm, &bars->kv_full[slot], 64 * h, kv_head, row);
             if (++slot == kStages) {
               slot = 0;
               phase ^= 1;
@@ -492,7 +503,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (!first) {
               // S_full for this key tile implies the previous PV of this tile has completed, so O is quiescent.
 #pragma unroll
-              for (int c = 0; c < 128; c += 32) {
+              for (int c = 0; c < kD; c += 32) {
                 uint32_t orr[32];
                 tmem_ld32(t_o + c, orr);
                 tmem_ld_wait();
@@ -506,51 +517,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * scale_log2;
           turn_wait();
           RFA_STAMP(stamper, xi, 8 + 5 * t);
-          // exp2(s * c - m * c) on packed pairs.  MUFU.EX2 alone (16 lanes per SM) would cost 1024 cycles per
-          // 128x128 tile per warp and bound the whole kernel, so kPolyOf4 of every 4 pairs are evaluated with
-          // a polynomial on the FMA pipes instead (masked tiles keep exact zeros by staying on the MUFU path).
+          // exp2(s * c - m * c) on packed pairs (FFMA2 for the scaling, MUFU.EX2 for the exponential; a polynomial
+          // exp2 on the FMA pipes for a share of the elements was measured twice on B200 - round 1 and again after
+          // the round-2 pipeline change, profiles/r2/trip_fwd_tuning.log - and never beat MUFU-only, so it is gone).
           const uint64_t sc2 = pack2(scale_log2, scale_log2), nmc2 = pack2(-mc, -mc);
           uint64_t lsum = pack2(0.f, 0.f);
-          auto exp_chunks = [&](auto use_poly) {
 #pragma unroll
-            for (int c = 0; c < 128; c += 32) {
-              uint32_t pk[16];
-              [[maybe_unused]] float pe0 = 0.f, pe1 = 0.f;  // fp8 only: the even pair waiting for its odd partner
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t pk[16];
+            [[maybe_unused]] float pe0 = 0.f, pe1 = 0.f;  // fp8 only: the even pair waiting for its odd partner
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const uint64_t x = ffma2(pack2(s[c + 2 * i], s[c + 2 * i + 1]), sc2, nmc2);
-                float e0, e1;
-                if (decltype(use_poly)::value && (i & 3) < kPolyOf4) {
-                  exp2_poly2(x, e0, e1);
-                } else {
-                  float x0, x1;
-                  unpack2(x, x0, x1);
-                  e0 = fast_exp2(x0);
-                  e1 = fast_exp2(x1);
-                }
-                lsum = fadd2(lsum, pack2(e0, e1));
-                if constexpr (E::kFp8) {
-                  if (i & 1) {
-                    pk[i >> 1] = pack4_e4m3(pe0, pe1, e0, e1);
-                  } else {
-                    pe0 = e0;
-                    pe1 = e1;
-                  }
-                } else {
-                  pk[i] = Pack2<T>::pack(e0, e1);
-                }
-              }
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t x = ffma2(pack2(s[c + 2 * i], s[c + 2 * i + 1]), sc2, nmc2);
+              float x0, x1;
+              unpack2(x, x0, x1);
+              const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+              lsum = fadd2(lsum, pack2(e0, e1));
               if constexpr (E::kFp8) {
-                tmem_st8(t_s + (c >> 2), pk);  // 32 e4m3 = 8 columns per 32 scores
+                if (i & 1) {
+                  pk[i >> 1] = pack4_e4m3(pe0, pe1, e0, e1);
+                } else {
+                  pe0 = e0;
+                  pe1 = e1;
+                }
               } else {
-                tmem_st16(t_s + (c >> 1), pk);
+                pk[i] = Pack2<T>::pack(e0, e1);
               }
             }
-          };
-          if (masked) {
-            exp_chunks(std::false_type{});
-          } else {
-            exp_chunks(std::true_type{});
+            if constexpr (E::kFp8) {
+              tmem_st8(t_s + (c >> 2), pk);  // 32 e4m3 = 8 columns per 32 scores
+            } else {
+              tmem_st16(t_s + (c >> 1), pk);
+            }
           }
           float l0, l1;
           unpack2(lsum, l0, l1);
@@ -575,7 +573,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float inv = l > 0.f ? 1.0f / l : 0.f;
         if constexpr (E::kFp8) inv *= p.head_scale_v[kv_head];
 #pragma unroll
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < kD; c += 32) {
           uint32_t orr[32];
           tmem_ld32(t_o + c, orr);
           tmem_ld_wait();
@@ -594,7 +592,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       } else if (row_ok) {
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int c = 0; c < 128; c += 8) *reinterpret_cast<uint4*>(out_row + c) = z;
+        for (int c = 0; c < kD; c += 8) *reinterpret_cast<uint4*>(out_row + c) = z;
       }
       if (row_ok) {
         const float lse = l > 0.f ? m_ref * scale + __logf(l) : -CUDART_INF_F;
@@ -620,37 +618,35 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
   if (p.sig.world > 0) set_peer_timeout_from_env();
   CUtensorMap tq, tk, tv, tks, tvs;
   const int eb = dtype == kDtypeE4M3 ? 1 : 2;
-  if (dtype == kDtypeE4M3 && (p.head_scale_qk == nullptr || p.head_scale_v == nullptr || p.seg_lo != nullptr))
-    return "fp8 forward needs per-head descales and does not support sliding windows yet";
-  if (const char* e = make_tensor_map(&tq, q, eb, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tk, k, eb, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tv, v, eb, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tks, k_stage, eb, fwd::kTile, fwd::kD)) return e;
-  if (const char* e = make_tensor_map(&tvs, v_stage, eb, fwd::kTile, fwd::kD)) return e;
+  const int d = p.head_dim;
+  if (d != 64 && d != 128) return "the sm_100a forward is instantiated for head_dim 64 and 128";
+  if (dtype == kDtypeE4M3 && (p.head_scale_qk == nullptr || p.head_scale_v == nullptr || p.seg_lo != nullptr || d != 128))
+    return "fp8 forward needs per-head descales and head_dim 128, and does not support sliding windows yet";
+  if (const char* e = make_tensor_map(&tq, q, eb, fwd::kTile, d)) return e;
+  if (const char* e = make_tensor_map(&tk, k, eb, fwd::kTile, d)) return e;
+  if (const char* e = make_tensor_map(&tv, v, eb, fwd::kTile, d)) return e;
+  if (const char* e = make_tensor_map(&tks, k_stage, eb, fwd::kTile, d)) return e;
+  if (const char* e = make_tensor_map(&tvs, v_stage, eb, fwd::kTile, d)) return e;
   dim3 grid(n_blocks, 1, 1), block(fwd::kThreads, 1, 1);
   cudaError_t err = cudaSuccess;
-  static const int poly = [] {
-    const char* e = std::getenv("RFA_B200_POLY_EXP");
-    const int v = e ? std::atoi(e) : kDefaultPolyOf4;
-    return v < 0 ? 0 : (v > 2 ? 2 : v);
-  }();
-  auto launch = [&](auto kern) {
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
-    if (err == cudaSuccess) kern<<<grid, block, fwd::kSmemBytes, stream>>>(tq, tk, tv, tks, tvs, p);
+  auto launch = [&](auto kern, int smem) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err == cudaSuccess) kern<<<grid, block, smem, stream>>>(tq, tk, tv, tks, tvs, p);
   };
-  if (dtype == kDtypeE4M3) {  // experimental fp8 forward (e4m3 in, bf16 out)
-    launch(fwd::attn_fwd_kernel<fwd::Fp8E4M3, 0, false>);
+  auto pick = [&](auto tag, auto window) {
+    using T = decltype(tag);
+    constexpr bool kW = decltype(window)::value;
+    if (d == 128) launch(fwd::attn_fwd_kernel<T, kW, 128>, fwd::smem_bytes<128>());
+    else launch(fwd::attn_fwd_kernel<T, kW, 64>, fwd::smem_bytes<64>());
+  };
+  if (dtype == kDtypeE4M3) {  // fp8 forward (e4m3 in, bf16 out)
+    launch(fwd::attn_fwd_kernel<fwd::Fp8E4M3, false, 128>, fwd::smem_bytes<128>());
   } else if (p.seg_lo != nullptr) {  // sliding-window tables: the lower band edge is masked in-kernel
-    if (dtype == kDtypeBF16) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0, true>);
-    else launch(fwd::attn_fwd_kernel<__half, 0, true>);
-  } else if (dtype == kDtypeBF16) {
-    if (poly == 0) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 0, false>);
-    else if (poly == 1) launch(fwd::attn_fwd_kernel<__nv_bfloat16, 1, false>);
-    else launch(fwd::attn_fwd_kernel<__nv_bfloat16, 2, false>);
+    if (dtype == kDtypeBF16) pick(__nv_bfloat16{}, std::true_type{});
+    else pick(__half{}, std::true_type{});
   } else {
-    if (poly == 0) launch(fwd::attn_fwd_kernel<__half, 0, false>);
-    else if (poly == 1) launch(fwd::attn_fwd_kernel<__half, 1, false>);
-    else launch(fwd::attn_fwd_kernel<__half, 2, false>);
+    if (dtype == kDtypeBF16) pick(__nv_bfloat16{}, std::false_type{});
+    else pick(__half{}, std::false_type{});
   }
   if (err != cudaSuccess) return cudaGetErrorString(err);
   err = cudaGetLastError();

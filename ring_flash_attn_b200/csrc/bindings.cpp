@@ -21,7 +21,7 @@ int dtype_code(const at::Tensor& t) {
 TensorView view3(const at::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
   TORCH_CHECK(t.dim() == 3, name, " must be (rows, heads, head_dim)");
-  TORCH_CHECK(t.size(2) == 128, name, ": the sm_100a kernels support head_dim == 128 only");
+  TORCH_CHECK(t.size(2) == 128 || t.size(2) == 64, name, ": the sm_100a kernels are instantiated for head_dim 64 and 128");
   TORCH_CHECK(t.stride(2) == 1, name, ": last dimension must be contiguous");
   return TensorView{t.data_ptr(), t.size(0), static_cast<int>(t.size(1)), t.stride(0), t.stride(1)};
 }
@@ -48,7 +48,8 @@ struct FusedCtx {
 void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, const at::Tensor& k, const at::Tensor& v) {
   TORCH_CHECK(c.world <= rfa::kMaxRanks, "too many ranks for the fused path");
   TORCH_CHECK(c.push_tasks.scalar_type() == at::kLong && c.push_tasks.is_contiguous());
-  TORCH_CHECK(k.stride(1) == 128 && v.stride(1) == 128, "K/V heads must be contiguous inside a row for the push path");
+  TORCH_CHECK(k.stride(1) == k.size(2) && v.stride(1) == v.size(2),
+              "K/V heads must be contiguous inside a row for the push path");
   uint32_t* cnt = reinterpret_cast<uint32_t*>(c.counters.data_ptr());
   pp.world = static_cast<int>(c.world);
   pp.rows_cap = static_cast<int>(c.rows_cap);
@@ -134,6 +135,8 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   p.lse_S = static_cast<int>(lse_S);
   p.hq = static_cast<int>(q.size(1));
   p.hkv = static_cast<int>(k.size(1));
+  p.head_dim = static_cast<int>(q.size(2));
+  TORCH_CHECK(k.size(2) == q.size(2) && v.size(2) == q.size(2) && out.size(2) == q.size(2), "head_dim mismatch");
   p.scale = static_cast<float>(scale);
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
   p.n_items = static_cast<int>(items.size(0));
@@ -206,7 +209,8 @@ void attn_bwd_delta(const at::Tensor& out, const at::Tensor& dout, at::Tensor& d
   const c10::cuda::CUDAGuard guard(out.device());
   TORCH_CHECK(delta.is_contiguous() && delta.scalar_type() == at::kFloat);
   check(rfa::attn_bwd_delta_launch(dtype_code(out), view3(out, "out"), view3(dout, "dout"), delta.data_ptr<float>(),
-                                   static_cast<int>(lse_S), at::cuda::getCurrentCUDAStream()));
+                                   static_cast<int>(lse_S), static_cast<int>(out.size(2)),
+                                   at::cuda::getCurrentCUDAStream()));
 }
 
 void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor& k, const at::Tensor& v,
@@ -216,7 +220,7 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
   const c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(qsegs.scalar_type() == at::kInt && qsegs.is_cuda() && qsegs.is_contiguous() && qsegs.size(1) == 4);
-  TORCH_CHECK(dq_accum.scalar_type() == at::kFloat && dq_accum.dim() == 3 && dq_accum.size(2) == 128 &&
+  TORCH_CHECK(dq_accum.scalar_type() == at::kFloat && dq_accum.dim() == 3 && dq_accum.size(2) == q.size(2) &&
               dq_accum.stride(2) == 1);
   if (fc == nullptr) {
     TORCH_CHECK(dk.has_value() && dv.has_value());
@@ -236,6 +240,7 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
   p.lse_S = static_cast<int>(lse_S);
   p.hq = static_cast<int>(q.size(1));
   p.hkv = static_cast<int>(k.size(1));
+  p.head_dim = static_cast<int>(q.size(2));
   p.scale = static_cast<float>(scale);
   p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
   TensorView dqv{dq_accum.data_ptr(), dq_accum.size(0), static_cast<int>(dq_accum.size(1)), dq_accum.stride(0),
@@ -248,6 +253,13 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
     p.ready_epoch = static_cast<uint32_t>(fc->epoch);
     fill_push(p.push, p.sig, *fc, k, v);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(fc->counters.data_ptr());
+    {
+      static const int item_major = [] {
+        const char* e = std::getenv("RFA_B200_BWD_TILE_MAJOR");
+        return e ? std::atoi(e) : 1;
+      }();
+      p.item_major = item_major;
+    }
     p.dkv.my_pad = reinterpret_cast<uint32_t*>(fc->my_pad.data_ptr());
     p.dkv.sent_count = cnt + 32;
     p.dkv.epoch = static_cast<uint32_t>(fc->epoch);

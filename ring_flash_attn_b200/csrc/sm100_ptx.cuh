@@ -343,26 +343,6 @@ __device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// 2^x for a pair of x <= 0 on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5],
-// degree-3 minimax polynomial for 2^f (max rel. err 7.5e-5, far below bf16 resolution), exponent patched in
-// with one LEA per element.  Inputs below -126 are clamped (result ~1e-38 instead of 0).
-__device__ __forceinline__ void exp2_poly2(uint64_t x, float& e0, float& e1) {
-  float x0, x1;
-  unpack2(x, x0, x1);
-  x = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
-  const uint64_t magic = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23: integer part lands in the low mantissa bits
-  const uint64_t r = fadd2(x, magic);
-  const uint64_t f = fsub2(x, fsub2(r, magic));
-  uint64_t p = ffma2(f, pack2(0.0551716685f, 0.0551716685f), pack2(0.2426111251f, 0.2426111251f));
-  p = ffma2(p, f, pack2(0.6932609677f, 0.6932609677f));
-  p = ffma2(p, f, pack2(0.9999280572f, 0.9999280572f));
-  float p0, p1, r0, r1;
-  unpack2(p, p0, p1);
-  unpack2(r, r0, r1);
-  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
-  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
-}
-
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -26,8 +26,11 @@ Q_ITEM_ROWS = 256  # rows per forward CTA (two 128-row MMA tiles)
 K_TILE_ROWS = 128  # keys per backward CTA
 
 
+KERNEL_HEAD_DIMS = (64, 128)  # instantiations of both kernels (template parameter kD)
+
+
 def supported(q: torch.Tensor, k: torch.Tensor) -> bool:
-    return q.shape[-1] == 128 and q.dtype in (torch.bfloat16, torch.float16) and k.dtype == q.dtype
+    return q.shape[-1] in KERNEL_HEAD_DIMS and q.dtype in (torch.bfloat16, torch.float16) and k.dtype == q.dtype
 
 
 def _diag(d: Optional[int]) -> int:

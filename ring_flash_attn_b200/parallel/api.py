@@ -41,27 +41,29 @@ __all__ = [
 # the op: one torch.library custom op for every scheme (parallel/ops.py)
 # ----------------------------------------------------------------------------------------------
 
-KERNEL_HEAD_DIM = 128  # the sm_100a kernels are specialised for this head size
+KERNEL_HEAD_DIMS = (64, 128)  # the sm_100a kernels are instantiated for these head sizes
+KERNEL_HEAD_DIM = KERNEL_HEAD_DIMS[-1]
 
 
 def _pad_head_dim(q) -> int:
-    """Columns of zero padding that bring the head size to the kernels' 128.
+    """Columns of zero padding that bring the head size to the next one the kernels are instantiated for (64, 128).
 
     Zero columns change neither Q.K^T nor the first ``d`` columns of P.V, and their gradients are exactly zero,
-    so a head size below 128 runs on the tcgen05 kernels (at the cost of the padded FLOPs) instead of dropping
-    to the dense torch blocks.  ``RFA_B200_PAD_HEAD_DIM=0`` disables it, ``=force`` applies it on any device
-    (used by the CPU tests)."""
+    so e.g. head size 80 or 96 runs on the tcgen05 kernels as 128 (at the cost of the padded FLOPs) and 32 as 64,
+    instead of dropping to the dense torch blocks.  ``RFA_B200_PAD_HEAD_DIM=0`` disables it, ``=force`` applies it
+    on any device (used by the CPU tests)."""
     mode = os.environ.get("RFA_B200_PAD_HEAD_DIM", "1")
     d = q.shape[-1]
-    if mode == "0" or d >= KERNEL_HEAD_DIM:
+    if mode == "0" or d >= KERNEL_HEAD_DIM or d in KERNEL_HEAD_DIMS:
         return 0
+    target = min(x for x in KERNEL_HEAD_DIMS if x > d)
     if mode == "force":
-        return KERNEL_HEAD_DIM - d
+        return target - d
     if q.dtype in (torch.bfloat16, torch.float16):
         from ..ops import cuda_ext
 
         if cuda_ext.available_for(q):
-            return KERNEL_HEAD_DIM - d
+            return target - d
     return 0
 
 

@@ -326,11 +326,56 @@ def _warn_once(msg: str) -> None:
         warnings.warn("ring_flash_attn_b200: " + msg, RuntimeWarning, stacklevel=3)
 
 
+def fused_heads_per_pass(plan: CPPlan, k: torch.Tensor, heads_k_stride: int) -> int:
+    """How many kv heads one fused launch of the llama3 scheme covers.
+
+    The reference gathers ``heads_k_stride`` kv heads at a time so that the gathered K/V buffer stays bounded
+    (/root/reference/ring_flash_attn/llama3_flash_attn_varlen.py:89-115).  On the fused path the quantity that grows
+    with the number of heads is the peer-mapped staging buffer (every source's rows x heads, two call parities), so
+    ``heads_k_stride`` is the granularity and ``RFA_B200_STAGE_BUDGET_MB`` (default 8192) the cap: as many multiples of
+    ``heads_k_stride`` heads per launch as fit the budget - all of them when memory allows, because one launch over
+    all heads is the fastest schedule.  ``RFA_B200_LLAMA3_HEAD_GROUPS=strict`` uses exactly ``heads_k_stride`` heads
+    per launch (the reference's memory behaviour)."""
+    hkv = k.shape[1]
+    stride = max(1, min(int(heads_k_stride), hkv))
+    if hkv % stride:
+        raise ValueError(f"heads_k_stride={stride} must divide the number of kv heads ({hkv})")
+    if os.environ.get("RFA_B200_LLAMA3_HEAD_GROUPS", "auto") == "strict":
+        return stride
+    budget = int(os.environ.get("RFA_B200_STAGE_BUDGET_MB", "8192")) << 20
+    per_head = 2 * 2 * plan.world * plan.kv_rows * k.shape[2] * k.element_size()  # parities x (K, V) x sources x rows
+    g = hkv
+    while g > stride and g * per_head > budget:
+        g -= stride
+        while g > stride and hkv % g:
+            g -= stride
+    return g
+
+
+def _fused_by_head_groups(plan, k, heads_k_stride, transport):
+    """(heads per pass) when the fused llama3 path must run in several passes over kv-head groups, else None."""
+    if transport != "allgather" or plan.world == 1:
+        return None
+    g = fused_heads_per_pass(plan, k, heads_k_stride)
+    return g if g < k.shape[1] else None
+
+
 def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_stride: int = 1):
     if _fused_ok(q, k, group, plan):
         from . import fused
 
-        return fused.forward(plan, q, k, v, scale, group)
+        g = _fused_by_head_groups(plan, k, heads_k_stride, transport)
+        if g is None:
+            return fused.forward(plan, q, k, v, scale, group)
+        rep = q.shape[1] // k.shape[1]
+        outs, lses = [], []
+        for h0 in range(0, k.shape[1], g):  # one fused launch per group of kv heads: staging holds g heads only
+            qs = slice(h0 * rep, (h0 + g) * rep)
+            with _head_group_scales(qs, slice(h0, h0 + g)):
+                o, l = fused.forward(plan, q[:, qs], k[:, h0:h0 + g], v[:, h0:h0 + g], scale, group)
+            outs.append(o)
+            lses.append(l)
+        return torch.cat(outs, dim=1), torch.cat(lses, dim=0)
     if transport == "allgather":
         return allgather_forward(plan, q, k, v, scale, group, heads_k_stride)
     return ring_forward(plan, q, k, v, scale, group)
@@ -346,7 +391,19 @@ def cp_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, transport="
     if _fused_ok(q, k, group, plan):
         from . import fused
 
-        return fused.backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)
+        g = _fused_by_head_groups(plan, k, heads_k_stride, transport)
+        if g is None:
+            return fused.backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)
+        rep = q.shape[1] // k.shape[1]
+        dqs, dks, dvs = [], [], []
+        for h0 in range(0, k.shape[1], g):
+            qs = slice(h0 * rep, (h0 + g) * rep)
+            dq_g, dk_g, dv_g = fused.backward(plan, dout[:, qs], q[:, qs], k[:, h0:h0 + g], v[:, h0:h0 + g],
+                                              out[:, qs], lse[qs], scale, group, deterministic)
+            dqs.append(dq_g)
+            dks.append(dk_g)
+            dvs.append(dv_g)
+        return torch.cat(dqs, dim=1), torch.cat(dks, dim=1), torch.cat(dvs, dim=1)
     if transport == "allgather":
         return allgather_backward(plan, dout, q, k, v, out, lse, scale, group, heads_k_stride, deterministic)
     return ring_backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)

@@ -88,12 +88,12 @@ class PeerContext:
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
 
-    def ensure_stage(self, rows: int, hkv: int, dtype) -> None:
+    def ensure_stage(self, rows: int, hkv: int, dtype, head_dim: int = 128) -> None:
         """Grow-only staging capacity (two call-parity halves).  The per-call layout is derived from the
         current shapes, so batches of different length reuse the same mapping; a (collective) reallocation
         only happens when a call needs more bytes than any call before it."""
         esize = torch.empty((), dtype=dtype).element_size()
-        need_half = 2 * self.world * rows * hkv * 128 * esize  # [K|V][slot][rows] for one parity
+        need_half = 2 * self.world * rows * hkv * head_dim * esize  # [K|V][slot][rows] for one parity
         if self.stage is not None and need_half <= self.stage_half:
             return
         self._quiesce()
@@ -103,10 +103,10 @@ class PeerContext:
         self.stage = PeerBuffer(2 * self.stage_half, self.device, self.group)
         self._quiesce()
 
-    def ensure_inbox(self, rows: int, hkv: int, dtype) -> None:
+    def ensure_inbox(self, rows: int, hkv: int, dtype, head_dim: int = 128) -> None:
         esize = torch.empty((), dtype=dtype).element_size()
-        need = self.world * 2 * rows * hkv * 128 * esize
-        self.inbox_kv_stride = rows * hkv * 128  # elements
+        need = self.world * 2 * rows * hkv * head_dim * esize
+        self.inbox_kv_stride = rows * hkv * head_dim  # elements
         self.inbox_slot_stride = 2 * self.inbox_kv_stride
         if self.inbox is not None and need <= self.inbox.nbytes:
             return
@@ -134,16 +134,16 @@ class PeerContext:
     # -- per-call context object --------------------------------------------------------------------
     def fused_ctx(self, plan: CPPlan, k: torch.Tensor, n_compute_ctas: int, dyn_needs: Optional[torch.Tensor] = None):
         C = cuda_ext.load()
-        rows, hkv = plan.kv_rows, k.shape[1]
+        rows, hkv, d = plan.kv_rows, k.shape[1], k.shape[2]
         esize = k.element_size()
-        row_bytes = hkv * 128 * esize
+        row_bytes = hkv * d * esize
         self.epoch += 1
         parity = self.epoch & 1
         fc = C.FusedCtx()
         half = parity * self.stage_half
         region = self.world * rows * row_bytes
-        fc.k_stage = self.stage.tensor(half, (self.world * rows, hkv, 128), k.dtype)
-        fc.v_stage = self.stage.tensor(half + region, (self.world * rows, hkv, 128), k.dtype)
+        fc.k_stage = self.stage.tensor(half, (self.world * rows, hkv, d), k.dtype)
+        fc.v_stage = self.stage.tensor(half + region, (self.world * rows, hkv, d), k.dtype)
         fc.my_pad = self.pad_tensor
         fc.rows_cap, fc.region_bytes = rows, region
         if dyn_needs is None:
@@ -337,7 +337,7 @@ def push_tasks(plan: CPPlan, ctx: PeerContext, row_bytes: int, device):
 
 def _kv_ok(t: torch.Tensor) -> torch.Tensor:
     t = attn_cuda._rows3(t)
-    return t if t.stride(1) == 128 else t.contiguous()
+    return t if t.stride(1) == t.shape[2] else t.contiguous()
 
 
 def fused_forward(plan: CPPlan, q, k, v, scale, group):
@@ -345,7 +345,7 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
     C = cuda_ext.load()
     k, v = _kv_ok(k), _kv_ok(v)
     rows, hq = plan.kv_rows, q.shape[1]
-    ctx.ensure_stage(rows, k.shape[1], k.dtype)
+    ctx.ensure_stage(rows, k.shape[1], k.dtype, k.shape[2])
     offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
     flags = {s: s for s in range(plan.world) if s != plan.rank}
     window = attn_cuda.has_window(plan.segments)
@@ -362,7 +362,8 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
         items, segs, covered = attn_cuda.fwd_tables(plan, plan.segments, offsets, q.device, ("fused",), flags)
     dyn = needs_gathered(plan, ctx, q.device) if is_dynamic(plan) else None
     tq = q.shape[0]
-    out = (torch.empty if covered else torch.zeros)((tq, hq, 128), dtype=attn_cuda.out_dtype(q), device=q.device)
+    out = (torch.empty if covered else torch.zeros)((tq, hq, q.shape[2]), dtype=attn_cuda.out_dtype(q),
+                                                    device=q.device)
     lse = torch.empty((hq, tq), dtype=torch.float32, device=q.device)
     if not covered:
         lse.fill_(float("-inf"))
@@ -418,8 +419,8 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     C = cuda_ext.load()
     k, v = _kv_ok(k), _kv_ok(v)
     rows, hkv = plan.kv_rows, k.shape[1]
-    ctx.ensure_stage(rows, hkv, k.dtype)
-    ctx.ensure_inbox(rows, hkv, k.dtype)
+    ctx.ensure_stage(rows, hkv, k.dtype, k.shape[2])
+    ctx.ensure_inbox(rows, hkv, k.dtype, k.shape[2])
     offsets = {s: (0 if s == plan.rank else s * rows) for s in range(plan.world)}
     flags = {s: s for s in range(plan.world) if s != plan.rank}
     window = attn_cuda.has_window(plan.segments)
@@ -455,8 +456,8 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     cuda_ext.note_launch()
     # owner-side reduction of the inbox (waits for the peers' "gradients landed" epochs on the device)
     tasks = reduce_tasks(plan, ctx, q.device)
-    dk = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
-    dv = torch.empty((rows, hkv, 128), dtype=k.dtype, device=q.device)
+    dk = torch.empty((rows, hkv, k.shape[2]), dtype=k.dtype, device=q.device)
+    dv = torch.empty((rows, hkv, k.shape[2]), dtype=k.dtype, device=q.device)
     inbox = ctx.inbox.tensor(0, (ctx.world * ctx.inbox_slot_stride,), k.dtype)
     ctx.ticket_cum = (ctx.ticket_cum + 128 * int(tasks.shape[0])) & MASK32  # kReduceBlocksPerTask
     C.reduce_dkv(inbox, ctx.inbox_slot_stride, ctx.inbox_kv_stride, dk, dv, tasks, fc, ctx.ticket_cum)

@@ -181,10 +181,11 @@ def test_world1_sliding_window_on_device():
     assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
 
 
-@pytest.mark.parametrize("d", [64, 96])
+@pytest.mark.parametrize("d", [32, 64, 96])
 def test_world1_small_head_dim_runs_on_kernels(d):
-    """head_dim < 128 is zero-padded to the kernels' head size (parallel/api.py:_pad_head_dim) - still our
-    launches (counter moves), still the oracle's numbers with the caller's 1/sqrt(d) scale."""
+    """head_dim 64 has its own kernel instantiations (template parameter kD); other sizes below 128 are zero-padded
+    to the next instantiated size (parallel/api.py:_pad_head_dim) - still our launches (counter moves), still the
+    oracle's numbers with the caller's 1/sqrt(d) scale."""
     from ring_flash_attn_b200.ops import cuda_ext
 
     torch.manual_seed(0)
@@ -344,3 +345,28 @@ def test_compile_fullgraph_world1(backend):
     assert cuda_ext.launch_counter().value >= before + 6, "compiled function did not reach the sm_100a kernels"
     torch.testing.assert_close(out.float(), ref.float(), atol=1e-2, rtol=1e-2)
     assert (qkv.grad.float() - g_ref.float()).abs().max().item() < 2e-2 * g_ref.float().abs().max().item() + 1e-2
+
+
+@pytest.mark.parametrize("window", [(-1, -1), (200, 0)])
+def test_head_dim_64_native(window):
+    """kD = 64 instantiations of both kernels: GQA, packed varlen documents with ragged tiles, sliding window."""
+    from ring_flash_attn_b200.ops import cuda_ext
+
+    torch.manual_seed(1)
+    T, H, HK, d = 1500, 8, 2, 64
+    cu = torch.tensor([0, 100, 101, 900, T], dtype=torch.int32, device="cuda")
+    q = torch.randn(T, H, d, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    kv = torch.randn(T, 2, HK, d, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(T, H, d, device="cuda").to(torch.bfloat16)
+    rq, rkv = q.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    ref, ref_lse = varlen_attention_oracle(rq, rkv[:, 0], rkv[:, 1], cu.cpu(), True, window_size=window)
+    ref.backward(dout.float())
+    before = cuda_ext.launch_counter().value
+    out, lse, _ = rfa.ring_flash_attn_varlen_kvpacked_func(q, kv, cu, 799, causal=True, window_size=window,
+                                                         return_attn_probs=True)
+    out.backward(dout)
+    assert cuda_ext.launch_counter().value >= before + 3 and out.shape == (T, H, d)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
+    assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
+    assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2

@@ -25,15 +25,15 @@ def _close(got, want, name, rel=5e-2, abs_=2e-2):
     assert err < lim, f"{name}: max err {err} > {lim}"
 
 
-def _batch_case(rank, world, scheme, causal, p2p, hq, hkv, s_local, iters):
+def _batch_case(rank, world, scheme, causal, p2p, hq, hkv, s_local, iters, d=128):
     os.environ["RFA_B200_DISABLE_P2P"] = "0" if p2p else "1"
     dev = torch.device("cuda", rank)
     torch.manual_seed(0)
     s = s_local * world
-    q = torch.randn(1, s, hq, 128, device=dev)
-    k = torch.randn(1, s, hkv, 128, device=dev)
-    v = torch.randn(1, s, hkv, 128, device=dev)
-    dout = torch.randn(1, s, hq, 128, device=dev)
+    q = torch.randn(1, s, hq, d, device=dev)
+    k = torch.randn(1, s, hkv, d, device=dev)
+    v = torch.randn(1, s, hkv, d, device=dev)
+    dout = torch.randn(1, s, hq, d, device=dev)
     for t in (q, k, v, dout):
         dist.broadcast(t, src=0)
     q, k, v, dout = (t.to(torch.bfloat16) for t in (q, k, v, dout))
@@ -63,6 +63,7 @@ def _all_batch_cases(rank, world, p2p):
     # one process group for every case: spawning + NCCL init dominates the test time otherwise
     for scheme, causal, hq, hkv, s_local in BATCH_CASES:
         _batch_case(rank, world, scheme, causal, p2p, hq, hkv, s_local, 3 if p2p else 1)
+    _batch_case(rank, world, "zigzag", True, p2p, 4, 2, 640, 2, d=64)  # kD = 64 instantiations, fused and fallback
 
 
 @pytest.mark.parametrize("p2p", [True, False])
@@ -127,6 +128,7 @@ def _varlen_case(rank, world, which, p2p):
         lq, lk, lv = (sh(t).detach().requires_grad_(True) for t in (q, k, v))
         if which == "llama3":
             cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu_t, True, rank, world)
+            cq, ck = cq.clone(), ck.clone()  # plain tensors: the fused path must not depend on prepare()'s objects
             out, lse, _ = rfa.llama3_flash_attn_varlen_func(lq, lk, lv, cq, ck, mq, mk, heads_k_stride=1,
                                                           local_k_slice=ks, causal=True, return_attn_probs=True)
         else:
@@ -291,3 +293,19 @@ def test_compiled_schemes_2gpu():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     run_distributed(_compiled_case, 2, backend="nccl")
+
+
+def _llama3_strict_groups(rank, world):
+    """heads_k_stride honoured literally (RFA_B200_LLAMA3_HEAD_GROUPS=strict): one fused launch per kv head, staging
+    sized for one head; also a hand-built (cloned) cu_seqlens - no attribute of prepare()'s tensors is needed."""
+    os.environ["RFA_B200_LLAMA3_HEAD_GROUPS"] = "strict"
+    try:
+        _varlen_case(rank, world, "llama3", True)
+    finally:
+        os.environ.pop("RFA_B200_LLAMA3_HEAD_GROUPS", None)
+
+
+def test_llama3_head_groups_2gpu():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_llama3_strict_groups, 2, backend="nccl")
