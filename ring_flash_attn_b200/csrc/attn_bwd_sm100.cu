@@ -135,7 +135,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // tile of head 1 that could already run.
   const int kv_head = p.item_major ? cta % p.hkv : cta / p.n_items;
   const int group = p.hq / p.hkv;
-  const BwdItem it = p.items[p.item_major ? cta / p.hkv : cta % p.n_items];
+  BwdItem it = p.items[p.item_major ? cta / p.hkv : cta % p.n_items];
+  if (p.flags & 4) it.seg_count = 0;  // timing experiment: K/V push + dK/dV return only
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -186,7 +187,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // land in the K | V area after the epilogue has started to stage those rows there)
       if (lane == 0 && total_tiles > 0) {
         const bool staged = it.flag >= 0 && p.ready_flags != nullptr;
-        if (staged) {
+        if (staged && !(p.flags & 2)) {
           wait_epoch(p.ready_flags + it.flag, p.ready_epoch, "bwd kv ready", p.sig.my_rank, it.flag);
           fence_proxy_async_all();
         }
@@ -699,6 +700,7 @@ const char* attn_bwd_launch(int dtype, const TensorView& q, const TensorView& do
   cudaError_t err;
   err = cudaSuccess;
   auto launch = [&](auto kern, int smem) {
+    if (p.push.n_ctas > 0 && smem < kPushSmemBytes) smem = kPushSmemBytes;  // (head dim 64: the push ring is larger)
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err == cudaSuccess) kern<<<grid, block, smem, stream>>>(tq, tdo, tk, tv, tks, tvs, tdq, p);
   };

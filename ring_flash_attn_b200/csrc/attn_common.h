@@ -139,9 +139,18 @@ struct FwdParams {
   const WorkItem* items;
   const KVSegment* segs;
   const int* seg_lo;  // sliding window only (else nullptr): per segment, key j visible to chunk row i iff j >= i + lo
-  const float* head_scale_qk;  // fp8 only: q_descale * k_descale per QUERY head (multiplies the softmax scale)
-  const float* head_scale_v;   // fp8 only: v_descale per KV head (multiplies the output)
-  int flags;  // tuning switches (RFA_B200_FWD_FLAGS): bit 0 = no turn-taking between the two softmax warpgroups
+  // fp8 only: block descales.  q_scale[(row / q_scale_block) * hq + head]; k_scale / v_scale[(r / kv_scale_block) * hkv +
+  // kv_head] with r = row in the K/V tensor the tile is read from (staging rows as they are; local rows + kv_scale_row0,
+  // i.e. the tables cover [world][rows] in fused launches); v_ref[kv_head] = the head's largest V descale.
+  const float* q_scale;
+  const float* k_scale;
+  const float* v_scale;
+  const float* v_ref;
+  int q_scale_block, kv_scale_block;
+  long long kv_scale_row0;
+  int flags;  // tuning / timing switches (RFA_B200_FWD_FLAGS): bit 0 = no turn-taking between the two softmax
+              // warpgroups; bit 1 = do not wait for remote K/V (compute-only timing, wrong numbers); bit 2 = no
+              // compute (communication-only timing)
   void* out;  // (rows, hq, 128) contiguous, input dtype
   float* lse;  // index = (row / lse_S) * hq * lse_S + head * lse_S + row % lse_S
   int lse_S;
@@ -193,6 +202,7 @@ struct BwdParams {
   int n_items;
   int window;  // != 0: BwdQSegment::lo is meaningful (selects the kernel variant that masks the lower band edge)
   int item_major;  // CTA numbering: 0 = head-major (one GPU), 1 = key-tile-major (fused launches, table in ring order)
+  int flags;       // timing switches (RFA_B200_BWD_FLAGS): bit 1 = do not wait for remote K/V, bit 2 = no compute
   unsigned long long* trace;  // RFA_TRACE builds only
   PushParams push;
   SignalParams sig;

@@ -75,8 +75,9 @@ struct Barriers {
 // Element traits.  Fp8E4M3 is the tag of the experimental fp8 forward (RFA_B200_FP8_KERNEL=1): q / k / v are e4m3
 // bytes, a tile is ONE 128-byte swizzle span per row (16 KB, loaded into the same 32 KB slots), both GEMMs are
 // kind::f8f6f4 with K = 32 per instruction, P is written back to tensor memory as e4m3 (four per column) and the
-// output is bf16.  Per-head descales (q*k folded into the softmax scale, v applied in the epilogue) come in
-// through FwdParams::head_scale_qk / head_scale_v.
+// output is bf16.  Block descales (q: per token block x head, k / v: per 128-token block x kv head, or coarser) come
+// in through FwdParams::q_scale / k_scale / v_scale; they are applied to the fp32 scores and folded into P, at no
+// extra tensor-core or memory cost.
 struct Fp8E4M3 {};
 template <typename T>
 struct Elem {
@@ -164,7 +165,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int head = cta / p.n_items;  // consecutive CTAs share a head => K/V tiles are reused out of L2
   const int kv_head = head / (p.hq / p.hkv);
-  const WorkItem it = p.items[cta % p.n_items];
+  WorkItem it = p.items[cta % p.n_items];
+  if (p.flags & 4) it.seg_count = 0;  // timing experiment: communication only (compute CTAs have nothing to do)
   const int n_rows0 = it.q_rows < kTile ? it.q_rows : kTile;
   const int n_rows1 = it.q_rows - n_rows0;
   const bool has_t1 = n_rows1 > 0;
@@ -214,7 +216,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const KVSegment sg = p.segs[it.seg_begin + si];
         const SegGeom g = seg_geom(sg, it);
         const bool staged = sg.flag >= 0 && p.ready_flags != nullptr;
-        if (g.n_tiles > 0 && staged) {
+        if (g.n_tiles > 0 && staged && !(p.flags & 2)) {  // (flags bit 1: timing experiment, compute only)
           wait_epoch(p.ready_flags + sg.flag, p.ready_epoch, "fwd kv ready", p.sig.my_rank, sg.flag);
           fence_proxy_async_all();
         }
@@ -404,14 +406,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t t_o = tmem + (t == 0 ? kColO0 : kColO1) + lane_addr;
     const int chunk_row = it.q_off + t * kTile + row_in_tile;  // row index inside the chunk (diagonal space)
 
-    // fp8: the per-head q*k descale rides on the softmax scale
-    float scale = p.scale, scale_log2 = p.scale_log2;
+    // Scores in log2 units are s * t2 with t2 = softmax_scale * log2(e); the running reference max m2 is kept in
+    // those units.  fp8 (block-scaled inputs): the descale of this query row (per token block x head) rides on t2
+    // for the whole row, the descale of the key block (128-token blocks x kv head, or per head) is multiplied in per
+    // key tile, and the V descale of the key block enters P as a ratio to the head's largest V descale (so that P
+    // stays in e4m3's normal range) with the reference value applied once in the epilogue.
+    float base_l2 = p.scale_log2;
+    [[maybe_unused]] float inv_vref = 1.f;
     if constexpr (E::kFp8) {
-      const float hs = p.head_scale_qk[head];
-      scale *= hs;
-      scale_log2 *= hs;
+      const int qrow = it.q_row0 + t * kTile + (row_in_tile < n_rows ? row_in_tile : 0);
+      base_l2 *= p.q_scale[static_cast<size_t>(qrow / p.q_scale_block) * p.hq + head];
+      inv_vref = 1.0f / p.v_ref[kv_head];
     }
-    float m_ref = -CUDART_INF_F;  // reference max (raw score units)
+    float m2 = -CUDART_INF_F;  // reference max (log2 units)
     float l = 0.f;
     bool first = true;
     uint32_t s_phase = 0;
@@ -440,9 +447,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       int xi = 0;
       [[maybe_unused]] const bool stamper = (threadIdx.x & 127) == 0;  // RFA_TRACE builds only
       for (int si = 0; si < it.seg_count; ++si) {
-        const SegGeom g = seg_geom(p.segs[it.seg_begin + si], it);
+        const KVSegment sg = p.segs[it.seg_begin + si];
+        const SegGeom g = seg_geom(sg, it);
         int seg_lo = 0;
         if constexpr (kWindow) seg_lo = p.seg_lo[it.seg_begin + si];
+        // fp8: row of the key tile in the scale tables (staged rows are indexed like the staging buffer, local rows
+        // are offset to this rank's slot)
+        [[maybe_unused]] const long long scale_row0 =
+            g.kv_row0 + ((sg.flag >= 0 && p.ready_flags != nullptr) ? 0ll : static_cast<long long>(p.kv_scale_row0));
         for (int jj = 0; jj < g.n_tiles; ++jj, ++xi) {
           if (!tile_active(g, it, t, jj)) {
             turn_wait();
@@ -491,14 +503,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mx2 = fmaxf(mx2, s[c + 2]);
             mx3 = fmaxf(mx3, s[c + 3]);
           }
-          const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+          float t2 = base_l2;
+          [[maybe_unused]] float log2_ratio = 0.f, inv_ratio = 1.f;
+          if constexpr (E::kFp8) {
+            const size_t sb = static_cast<size_t>((scale_row0 + static_cast<long long>(jj) * kTile) / p.kv_scale_block) *
+                                  p.hkv + kv_head;
+            t2 *= p.k_scale[sb];
+            const float ratio = p.v_scale[sb] * inv_vref;
+            log2_ratio = __log2f(ratio);
+            inv_ratio = 1.0f / ratio;
+          }
+          const float m_new = fmaxf(m2, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * t2);
           // lazy rescale: only move the reference max when it grew by more than the threshold
-          const bool need = (m_new - m_ref) * scale_log2 > kRescaleThreshold;
+          const bool need = (m_new - m2) > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            const float f = need ? fast_exp2((m_ref - m_new) * scale_log2) : 1.0f;
+            const float f = need ? fast_exp2(m2 - m_new) : 1.0f;
             if (need) {
               l *= f;
-              m_ref = m_new;
+              m2 = m_new;
             }
             if (!first) {
               // S_full for this key tile implies the previous PV of this tile has completed, so O is quiescent.
@@ -514,13 +536,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
           first = false;
-          const float mc = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * scale_log2;
+          const float mc = (m2 == -CUDART_INF_F ? 0.f : m2) - log2_ratio;
           turn_wait();
           RFA_STAMP(stamper, xi, 8 + 5 * t);
           // exp2(s * c - m * c) on packed pairs (FFMA2 for the scaling, MUFU.EX2 for the exponential; a polynomial
           // exp2 on the FMA pipes for a share of the elements was measured twice on B200 - round 1 and again after
           // the round-2 pipeline change, profiles/r2/trip_fwd_tuning.log - and never beat MUFU-only, so it is gone).
-          const uint64_t sc2 = pack2(scale_log2, scale_log2), nmc2 = pack2(-mc, -mc);
+          const uint64_t sc2 = pack2(t2, t2), nmc2 = pack2(-mc, -mc);
           uint64_t lsum = pack2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < 128; c += 32) {
@@ -554,7 +576,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           unpack2(lsum, l0, l1);
           turn_pass();
           RFA_STAMP(stamper, xi, 9 + 5 * t);
-          l += l0 + l1;
+          l += (l0 + l1) * inv_ratio;
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars->p_ready[t]);
@@ -571,7 +593,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&bars->o_done[t], 0);
         tc_fence_after();
         float inv = l > 0.f ? 1.0f / l : 0.f;
-        if constexpr (E::kFp8) inv *= p.head_scale_v[kv_head];
+        if constexpr (E::kFp8) inv *= p.v_ref[kv_head];
 #pragma unroll
         for (int c = 0; c < kD; c += 32) {
           uint32_t orr[32];
@@ -595,7 +617,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int c = 0; c < kD; c += 8) *reinterpret_cast<uint4*>(out_row + c) = z;
       }
       if (row_ok) {
-        const float lse = l > 0.f ? m_ref * scale + __logf(l) : -CUDART_INF_F;
+        const float lse = l > 0.f ? (m2 + __log2f(l)) * 0.6931471805599453f : -CUDART_INF_F;
         const size_t b = row / p.lse_S, sidx = row % p.lse_S;
         p.lse[(b * p.hq + head) * static_cast<size_t>(p.lse_S) + sidx] = lse;
       }
@@ -620,8 +642,10 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
   const int eb = dtype == kDtypeE4M3 ? 1 : 2;
   const int d = p.head_dim;
   if (d != 64 && d != 128) return "the sm_100a forward is instantiated for head_dim 64 and 128";
-  if (dtype == kDtypeE4M3 && (p.head_scale_qk == nullptr || p.head_scale_v == nullptr || p.seg_lo != nullptr || d != 128))
-    return "fp8 forward needs per-head descales and head_dim 128, and does not support sliding windows yet";
+  if (dtype == kDtypeE4M3 && (p.q_scale == nullptr || p.k_scale == nullptr || p.v_scale == nullptr ||
+                              p.v_ref == nullptr || p.q_scale_block < 1 || p.kv_scale_block < 1 ||
+                              p.seg_lo != nullptr || d != 128))
+    return "fp8 forward needs q / k / v descale tables and head_dim 128, and does not support sliding windows yet";
   if (const char* e = make_tensor_map(&tq, q, eb, fwd::kTile, d)) return e;
   if (const char* e = make_tensor_map(&tk, k, eb, fwd::kTile, d)) return e;
   if (const char* e = make_tensor_map(&tv, v, eb, fwd::kTile, d)) return e;
@@ -630,6 +654,7 @@ const char* attn_fwd_launch(int dtype, const TensorView& q, const TensorView& k,
   dim3 grid(n_blocks, 1, 1), block(fwd::kThreads, 1, 1);
   cudaError_t err = cudaSuccess;
   auto launch = [&](auto kern, int smem) {
+    if (p.push.n_ctas > 0 && smem < kPushSmemBytes) smem = kPushSmemBytes;  // (head dim 64: the push ring is larger)
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err == cudaSuccess) kern<<<grid, block, smem, stream>>>(tq, tk, tv, tks, tvs, p);
   };

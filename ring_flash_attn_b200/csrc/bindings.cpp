@@ -97,12 +97,17 @@ void fill_push(rfa::PushParams& pp, rfa::SignalParams& sg, const FusedCtx& c, co
   }
 }
 
+// Block descales of the fp8 forward (see FwdParams): tables are (blocks, heads) fp32.
+struct Fp8Scales {
+  at::Tensor q, k, v, v_ref;
+  int64_t q_block = 1, kv_block = 128, kv_row0 = 0;
+};
+
 void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
                    const at::Tensor& segs, at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale,
-                   const FusedCtx* fc, const at::Tensor* seg_lo = nullptr, const at::Tensor* scale_qk = nullptr,
-                   const at::Tensor* scale_v = nullptr) {
+                   const FusedCtx* fc, const at::Tensor* seg_lo = nullptr, const Fp8Scales* f8 = nullptr) {
   const c10::cuda::CUDAGuard guard(q.device());
-  const bool fp8 = scale_qk != nullptr;
+  const bool fp8 = f8 != nullptr;
   TORCH_CHECK(items.scalar_type() == at::kInt && items.is_cuda() && items.is_contiguous() && items.size(1) == 8);
   TORCH_CHECK(segs.scalar_type() == at::kInt && segs.is_cuda() && segs.is_contiguous() && segs.size(1) == 4);
   TORCH_CHECK(out.is_contiguous() && out.scalar_type() == (fp8 ? at::kBFloat16 : q.scalar_type()));
@@ -120,12 +125,24 @@ void attn_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   int dtype = 0;
   if (fp8) {
     TORCH_CHECK(q.scalar_type() == at::kFloat8_e4m3fn, "the fp8 forward takes float8_e4m3fn q / k / v");
-    TORCH_CHECK(scale_qk->scalar_type() == at::kFloat && scale_qk->is_cuda() && scale_qk->is_contiguous() &&
-                scale_qk->numel() == q.size(1), "head_scale_qk: one fp32 per query head");
-    TORCH_CHECK(scale_v->scalar_type() == at::kFloat && scale_v->is_cuda() && scale_v->is_contiguous() &&
-                scale_v->numel() == k.size(1), "head_scale_v: one fp32 per kv head");
-    p.head_scale_qk = scale_qk->data_ptr<float>();
-    p.head_scale_v = scale_v->data_ptr<float>();
+    auto table = [&](const at::Tensor& t, int64_t heads, const char* name) {
+      TORCH_CHECK(t.scalar_type() == at::kFloat && t.is_cuda() && t.is_contiguous() && t.dim() == 2 &&
+                  t.size(1) == heads && t.size(0) >= 1, name, ": fp32 (blocks, heads) descale table");
+      return t.data_ptr<float>();
+    };
+    p.q_scale = table(f8->q, q.size(1), "q_scale");
+    p.k_scale = table(f8->k, k.size(1), "k_scale");
+    p.v_scale = table(f8->v, k.size(1), "v_scale");
+    TORCH_CHECK(f8->v_ref.scalar_type() == at::kFloat && f8->v_ref.is_cuda() && f8->v_ref.is_contiguous() &&
+                f8->v_ref.numel() == k.size(1), "v_ref: one fp32 per kv head");
+    TORCH_CHECK(f8->k.size(0) == f8->v.size(0), "k_scale / v_scale must have the same number of blocks");
+    p.v_ref = f8->v_ref.data_ptr<float>();
+    TORCH_CHECK(f8->q_block >= 1 && f8->q.size(0) * f8->q_block >= q.size(0), "q_scale does not cover the query rows");
+    TORCH_CHECK(f8->kv_block >= 1 && (f8->kv_block % 128 == 0 || f8->k.size(0) == 1),
+                "k / v descale blocks must be multiples of 128 rows (one scale per key tile) or one per head");
+    p.q_scale_block = static_cast<int>(f8->q_block);
+    p.kv_scale_block = static_cast<int>(f8->kv_block);
+    p.kv_scale_row0 = f8->kv_row0;
     dtype = rfa::kDtypeE4M3;
   } else {
     dtype = dtype_code(q);
@@ -171,19 +188,25 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, con
   attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr);
 }
 
-// Experimental fp8 forward: q / k / v float8_e4m3fn (rows, heads, 128), out bf16.  head_scale_qk[h] = q_descale *
-// k_descale of query head h, head_scale_v[hk] = v_descale of kv head hk.
+// fp8 forward: q / k / v float8_e4m3fn (rows, heads, 128), out bf16, block descales:
+//   q_scale (ceil(rows / q_block), Hq), k_scale / v_scale (blocks of kv_block rows, Hkv), v_ref (Hkv) = max of v_scale
+//   per head; kv_row0 = row of local key row 0 inside the k / v scale tables.
 void attn_fwd_fp8(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
-                  const at::Tensor& segs, const at::Tensor& head_scale_qk, const at::Tensor& head_scale_v,
+                  const at::Tensor& segs, const at::Tensor& q_scale, int64_t q_block, const at::Tensor& k_scale,
+                  const at::Tensor& v_scale, int64_t kv_block, const at::Tensor& v_ref, int64_t kv_row0,
                   at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale) {
-  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr, nullptr, &head_scale_qk, &head_scale_v);
+  Fp8Scales f8{q_scale, k_scale, v_scale, v_ref, q_block, kv_block, kv_row0};
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, nullptr, nullptr, &f8);
 }
 
-// The same inside the fused multi-GPU launch (K/V rows travel as one byte per element).
+// The same inside the fused multi-GPU launch (K/V rows travel as one byte per element; the k / v tables cover
+// [world][rows] like the staging buffer).
 void attn_fwd_fused_fp8(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& items,
-                        const at::Tensor& segs, const at::Tensor& head_scale_qk, const at::Tensor& head_scale_v,
+                        const at::Tensor& segs, const at::Tensor& q_scale, int64_t q_block, const at::Tensor& k_scale,
+                        const at::Tensor& v_scale, int64_t kv_block, const at::Tensor& v_ref, int64_t kv_row0,
                         at::Tensor& out, at::Tensor& lse, int64_t lse_S, double scale, const FusedCtx& fc) {
-  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, &fc, nullptr, &head_scale_qk, &head_scale_v);
+  Fp8Scales f8{q_scale, k_scale, v_scale, v_ref, q_block, kv_block, kv_row0};
+  attn_fwd_impl(q, k, v, items, segs, out, lse, lse_S, scale, &fc, nullptr, &f8);
 }
 
 // Sliding-window launch: seg_lo[i] is the lower band offset of segment i (see FwdParams::seg_lo).
@@ -259,6 +282,11 @@ void attn_bwd_impl(const at::Tensor& q, const at::Tensor& dout, const at::Tensor
         return e ? std::atoi(e) : 1;
       }();
       p.item_major = item_major;
+      static const int bwd_flags = [] {
+        const char* e = std::getenv("RFA_B200_BWD_FLAGS");
+        return e ? std::atoi(e) : 0;
+      }();
+      p.flags = bwd_flags;
     }
     p.dkv.my_pad = reinterpret_cast<uint32_t*>(fc->my_pad.data_ptr());
     p.dkv.sent_count = cnt + 32;

@@ -155,6 +155,8 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uin
 constexpr int kPushBufBytes = 32768;
 constexpr int kPushBufs = 6;
 constexpr int kPushDepth = 3;  // loads in flight; with 6 buffers at most 2 store groups may still be reading
+// dynamic shared memory a launch with push CTAs must provide (buffers + mbarriers + 1 KB alignment slack)
+constexpr int kPushSmemBytes = kPushBufs * kPushBufBytes + 1024 + 1024;
 
 __device__ __forceinline__ void push_role_tma(const PushParams& pp, uint8_t* smem) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPushBufs * kPushBufBytes);
@@ -166,8 +168,31 @@ __device__ __forceinline__ void push_role_tma(const PushParams& pp, uint8_t* sme
   if (threadIdx.x != 0) return;
   const int rows_per_piece = pp.row_bytes >= kPushBufBytes ? 1 : kPushBufBytes / pp.row_bytes;
   uint32_t n_loaded = 0, n_stored = 0;  // global piece counters (ring position / parity)
+  // Completion is published per DESTINATION, not per task: the tasks of a CTA are sorted by destination, so the
+  // copy pipeline keeps running across task boundaries and is drained (all bytes written, system-scope fence)
+  // only when the destination changes.  Round 1 drained after every 512 KB task - a load-latency fill plus an
+  // NVLink write-completion wait per task, which at 8 GPUs (28 tasks per CTA) held the push to ~290 GB/s per GPU
+  // (profiles/r2/trip_diag8_compute_vs_comm.log).
+  int cur_dst = -1;
+  uint32_t pending = 0;  // finished tasks for cur_dst that are not yet counted
+  auto publish = [&]() {
+    if (pending == 0) return;
+    tma_store_wait<0>();  // every byte for this destination has been written
+    fence_proxy_async_all();
+    __threadfence_system();
+    const uint32_t old = atomicAdd(pp.sent_count + cur_dst, pending);
+    if (old + pending == pp.sent_target[cur_dst]) {
+      __threadfence_system();
+      st_release_sys(pp.peer_pads[cur_dst] + kPadKvReady + pp.my_rank, pp.epoch);
+    }
+    pending = 0;
+  };
   for (int ti = blockIdx.x; ti < pp.n_tasks; ti += pp.n_ctas) {
     const PushTask t = push_task_at(pp, ti);
+    if (t.dst != cur_dst) {
+      publish();
+      cur_dst = t.dst;
+    }
     if (pp.epoch > 2 && t.rows > 0)
       wait_epoch(pp.my_pad + kPadConsumed + t.dst, pp.epoch - 2, "staging reuse", pp.my_rank, t.dst);
     const long long pitch = pp.src_row_bytes[t.which];
@@ -202,15 +227,9 @@ __device__ __forceinline__ void push_role_tma(const PushParams& pp, uint8_t* sme
       ++n_stored;
       ++stv;
     }
-    tma_store_wait<0>();  // every byte of this task has been written
-    fence_proxy_async_all();
-    __threadfence_system();
-    const uint32_t old = atomicAdd(pp.sent_count + t.dst, 1u);
-    if (old + 1u == pp.sent_target[t.dst]) {
-      __threadfence_system();
-      st_release_sys(pp.peer_pads[t.dst] + kPadKvReady + pp.my_rank, pp.epoch);
-    }
+    ++pending;
   }
+  publish();
 }
 
 // Called by one thread of every compute CTA after the CTA has finished reading staged K/V.

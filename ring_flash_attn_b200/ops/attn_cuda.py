@@ -37,24 +37,70 @@ def _diag(d: Optional[int]) -> int:
     return DIAG_FULL if d is None else int(d)
 
 
-# ---- fp8 forward (e4m3 q / k / v with per-tensor or per-head descales; RFA_B200_FP8_KERNEL=0 disables) ----
-# The per-head descales of the running call; set by parallel/api.py around the engine call so that the
-# executors (which only know q / k / v) can hand them to the launch.
+# ---- fp8 forward (e4m3 q / k / v with block descales; RFA_B200_FP8_KERNEL=0 disables) -------------------
+# The descales of the running call; set by parallel/ops.py around the engine call so that the executors (which
+# only know q / k / v) can hand them to the launch.
 _FP8_STATE = threading.local()
 
 
+class Fp8Scales:
+    """Block descales in the form the forward kernel reads (csrc/attn_common.h: FwdParams::q_scale ...).
+
+    ``q``: (ceil(Tq / q_block), Hq) fp32, one per ``q_block`` consecutive token-major query rows and head.
+    ``k`` / ``v``: (n, Hkv) fp32, one per ``kv_block`` consecutive key rows and kv head, covering either this rank's
+    shard (``world_rows == 0``) or every rank's shard back to back (``world_rows`` = rows per shard; produced by
+    :meth:`gathered`), exactly like the staging buffer.  ``v_ref``: (Hkv,) the largest V descale of each head."""
+
+    def __init__(self, q, q_block, k, v, kv_block, v_ref=None, world_rows=0, kv_row0=0):
+        self.q, self.q_block, self.k, self.v, self.kv_block = q, int(q_block), k, v, int(kv_block)
+        self.v_ref = v.amax(dim=0).contiguous() if v_ref is None else v_ref
+        self.world_rows, self.kv_row0 = int(world_rows), int(kv_row0)
+
+    def gathered(self, group, rank: int, world: int, rows: int) -> "Fp8Scales":
+        """Tables of every rank's shard (two tiny all-gathers + one all-reduce on the current stream)."""
+        import torch.distributed as dist
+
+        if world == 1 or self.world_rows:
+            return self
+        if rows % self.kv_block and self.k.shape[0] != 1:
+            raise ValueError("k / v descale blocks must tile the local shard")
+        nb = self.k.shape[0]
+        k_all = torch.empty((world * nb, self.k.shape[1]), dtype=torch.float32, device=self.k.device)
+        v_all = torch.empty_like(k_all)
+        dist.all_gather_into_tensor(k_all, self.k.contiguous(), group=group)
+        dist.all_gather_into_tensor(v_all, self.v.contiguous(), group=group)
+        v_ref = self.v_ref.clone()
+        dist.all_reduce(v_ref, op=dist.ReduceOp.MAX, group=group)
+        kv_block = rows if nb == 1 else self.kv_block
+        return Fp8Scales(self.q, self.q_block, k_all, v_all, kv_block, v_ref, world_rows=rows, kv_row0=rank * rows)
+
+    def for_source(self, src: int) -> "Fp8Scales":
+        """Per-source launches of the torch.distributed transports read source ``src``'s K/V as a local tensor."""
+        if not self.world_rows:
+            return self
+        return Fp8Scales(self.q, self.q_block, self.k, self.v, self.kv_block, self.v_ref, self.world_rows,
+                         kv_row0=src * self.world_rows)
+
+    def heads(self, q_heads: slice, kv_heads: slice) -> "Fp8Scales":
+        return Fp8Scales(self.q[:, q_heads].contiguous(), self.q_block, self.k[:, kv_heads].contiguous(),
+                         self.v[:, kv_heads].contiguous(), self.kv_block, self.v_ref[kv_heads].contiguous(),
+                         self.world_rows, self.kv_row0)
+
+    def args(self):
+        return (self.q, self.q_block, self.k, self.v, self.kv_block, self.v_ref, self.kv_row0)
+
+
 @contextlib.contextmanager
-def fp8_scales(head_scale_qk: torch.Tensor, head_scale_v: torch.Tensor):
-    """head_scale_qk: (Hq,) fp32 = q_descale * k_descale per query head; head_scale_v: (Hkv,) fp32."""
+def fp8_scales(scales: "Fp8Scales"):
     prev = getattr(_FP8_STATE, "scales", None)
-    _FP8_STATE.scales = (head_scale_qk, head_scale_v)
+    _FP8_STATE.scales = scales
     try:
         yield
     finally:
         _FP8_STATE.scales = prev
 
 
-def current_fp8_scales():
+def current_fp8_scales() -> Optional["Fp8Scales"]:
     return getattr(_FP8_STATE, "scales", None)
 
 
@@ -392,8 +438,7 @@ def forward_launch(q, k, v, items, segs, covered, scale, out=None, lse=None):
             scales = current_fp8_scales()
             if scales is None:
                 raise RuntimeError("fp8 tensors reached the kernel launch without descales (attn_cuda.fp8_scales)")
-            C.attn_fwd_fp8(_rows3(q), _rows3(k), _rows3(v), items, segs, scales[0], scales[1], out, lse, tq,
-                           float(scale))
+            C.attn_fwd_fp8(_rows3(q), _rows3(k), _rows3(v), items, segs, *scales.args(), out, lse, tq, float(scale))
         else:
             C.attn_fwd(_rows3(q), _rows3(k), _rows3(v), items, segs, out, lse, tq, float(scale))
         cuda_ext.note_launch()

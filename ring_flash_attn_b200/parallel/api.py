@@ -77,38 +77,55 @@ def _cp_apply(q, k, v, scheme, spec, cu_a, cu_b, scale, group, deterministic, fp
         # fp8 forward kernel: e4m3 q / k / v straight into the kernels (and over the wire), bf16 out.
         # Forward only - fp8 tensors carry no gradient.
         with torch.no_grad():
-            return O.cp_attn_fwd(q, k, v, cu_a, cu_b, fp8[0], fp8[1], scheme, gname, spec, scale, deterministic)
+            return O.cp_attn_fwd(q, k, v, cu_a, cu_b, fp8[0], fp8[1], fp8[2], scheme, gname, spec, scale, deterministic)
     pad = _pad_head_dim(q)
     if pad:
         d = q.shape[-1]
         q, k, v = (torch.nn.functional.pad(t, (0, pad)) for t in (q, k, v))
-        out, lse = O.cp_attn_fwd(q, k, v, cu_a, cu_b, None, None, scheme, gname, spec, scale, deterministic)
+        out, lse = O.cp_attn_fwd(q, k, v, cu_a, cu_b, None, None, None, scheme, gname, spec, scale, deterministic)
         return out[..., :d].contiguous(), lse
-    return O.cp_attn_fwd(q, k, v, cu_a, cu_b, None, None, scheme, gname, spec, scale, deterministic)
+    return O.cp_attn_fwd(q, k, v, cu_a, cu_b, None, None, None, scheme, gname, spec, scale, deterministic)
 
 
 def _as_cu_tensor(cu) -> torch.Tensor:
     return cu if isinstance(cu, torch.Tensor) else torch.tensor([int(x) for x in cu], dtype=torch.int32)
 
 
-def _per_head(descale, x) -> Optional[torch.Tensor]:
-    """(H,) fp32 vector if ``descale`` is a per-tensor or per-head scale of ``x`` (heads at dim -2), else None."""
+def _scale_table(descale, x) -> Optional[torch.Tensor]:
+    """Canonical form of a descale the fp8 forward kernel can apply: an fp32 table ``(n_blocks, H)`` with one entry
+    per block of consecutive token-major rows and head (``x``: ``(B, S, H, D)`` or ``(T, H, D)``), or None when the
+    descale varies inside a row (MX-style per-32-element scales along head_dim) or does not tile the tokens evenly.
+
+    Accepted: None / python scalars / one-element tensors (per tensor), ``(1, 1, H, 1)`` (per head), ``(B, S/blk, H, 1)``
+    or ``(1, S/blk, H, 1)`` (per token block x head), ``(T/blk, H, 1)`` for packed layouts; H may be 1."""
     heads = x.shape[-2]
     if descale is None:
-        return torch.ones(heads, dtype=torch.float32, device=x.device)
+        return torch.ones((1, heads), dtype=torch.float32, device=x.device)
     if not isinstance(descale, torch.Tensor):
-        return torch.full((heads,), float(descale), dtype=torch.float32, device=x.device)
-    if descale.numel() == 1:
-        return descale.reshape(1).to(device=x.device, dtype=torch.float32).expand(heads).contiguous()
-    if descale.dim() == x.dim() and descale.shape[-2] == heads and descale.numel() == heads:
-        return descale.reshape(heads).to(device=x.device, dtype=torch.float32).contiguous()
-    return None
+        return torch.full((1, heads), float(descale), dtype=torch.float32, device=x.device)
+    d = descale.to(device=x.device, dtype=torch.float32)
+    if d.numel() == 1:
+        return d.reshape(1, 1).expand(1, heads).contiguous()
+    if d.dim() != x.dim() or d.shape[-1] != 1 or d.shape[-2] not in (1, heads):
+        return None
+    tokens, blocks = tuple(x.shape[:-2]), tuple(d.shape[:-2])
+    if any(n % s for n, s in zip(tokens, blocks)):
+        return None
+    if len(tokens) == 2:
+        if blocks[0] not in (1, tokens[0]):
+            return None
+        t = d.reshape(blocks[0], blocks[1], d.shape[-2]).expand(tokens[0], blocks[1], heads)
+        if blocks == (1, 1):
+            t = t[:1]
+        return t.reshape(-1, heads).contiguous()
+    return d.reshape(blocks[0], d.shape[-2]).expand(blocks[0], heads).contiguous()
 
 
 def _fp8_kernel_scales(q, k, v, dq, dk, dv, window_size):
-    """Descales for the experimental fp8 forward kernel, or None when the call does not qualify: opt-in
-    (``RFA_B200_FP8_KERNEL=1``), e4m3 q/k/v with head_dim 128 on a Blackwell GPU, per-tensor or per-head
-    descales, no sliding window.  Finer block scales take the dequantise-to-bf16 path."""
+    """Descale tables ``(q, k, v)`` for the fp8 forward kernel, or None when the call does not qualify: e4m3 q/k/v
+    with head_dim 128 on a Blackwell GPU, descales per tensor / head / token block x head (``_scale_table``), no
+    sliding window, ``RFA_B200_FP8_KERNEL`` != 0.  Whether the K / V blocks line up with the 128-key tiles of the plan
+    is decided inside the op (parallel/ops.py); anything else takes the dequantise-to-bf16 path."""
     if os.environ.get("RFA_B200_FP8_KERNEL", "2") == "0":
         return None
     if not (q.dtype == k.dtype == v.dtype == torch.float8_e4m3fn) or q.shape[-1] != 128:
@@ -119,18 +136,17 @@ def _fp8_kernel_scales(q, k, v, dq, dk, dv, window_size):
 
     if not cuda_ext.available_for(q):
         return None
-    sq, sk, sv = _per_head(dq, q), _per_head(dk, k), _per_head(dv, v)
-    if sq is None or sk is None or sv is None:
+    tq, tk, tv = _scale_table(dq, q), _scale_table(dk, k), _scale_table(dv, v)
+    if tq is None or tk is None or tv is None or tk.shape[0] != tv.shape[0]:
         return None
-    rep = q.shape[-2] // k.shape[-2]
-    return (sq * sk.repeat_interleave(rep)).contiguous(), sv
+    return tq, tk, tv
 
 
 def _maybe_dequant(q, k, v, descale, window_size=(-1, -1)):
     """fp8 extension (utils/fp8.py): ``descale`` is a tensor for a packed input or a (q, k, v) tuple.
 
-    Returns (q, k, v, fp8_scales): either dequantised tensors and None, or - for calls that qualify for the
-    experimental fp8 kernel - the untouched e4m3 tensors and their per-head descales."""
+    Returns (q, k, v, fp8_scales): either dequantised tensors and None, or - for calls that qualify for the fp8
+    forward kernel - the untouched e4m3 tensors and their descale tables."""
     from ..utils import fp8
 
     if not (fp8.is_fp8(q) or fp8.is_fp8(k) or fp8.is_fp8(v)):

@@ -92,7 +92,12 @@ def step_forward(plan: CPPlan, segs: List[Segment], q, k_src, v_src, scale, out,
     if _use_cuda_kernels(q, k_src) and _kernels_take(plan):
         from ..ops import attn_cuda
 
-        p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
+        sc = attn_cuda.current_fp8_scales()
+        if sc is not None and sc.world_rows:  # fp8: this launch reads source `src`'s rows as a local tensor
+            with attn_cuda.fp8_scales(sc.for_source(segs[0].src)):
+                p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
+        else:
+            p_out, p_lse = attn_cuda.segments_forward(plan, segs, q, k_src, v_src, scale)
         return merge_partial(out, lse, p_out, p_lse)
     if out is None:
         out = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
@@ -206,7 +211,7 @@ def _head_group_scales(q_heads: slice, kv_heads: slice):
         import contextlib
 
         return contextlib.nullcontext()
-    return attn_cuda.fp8_scales(scales[0][q_heads].contiguous(), scales[1][kv_heads].contiguous())
+    return attn_cuda.fp8_scales(scales.heads(q_heads, kv_heads))
 
 
 def _head_groups(hkv: int, stride: int):
@@ -361,6 +366,14 @@ def _fused_by_head_groups(plan, k, heads_k_stride, transport):
 
 
 def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_stride: int = 1):
+    if plan.world > 1 and _use_cuda_kernels(q, k):
+        from ..ops import attn_cuda
+
+        sc = attn_cuda.current_fp8_scales()
+        if sc is not None and not sc.world_rows:
+            # fp8: every transport reads remote K/V rows, so it needs their descales too (tables of all shards)
+            with attn_cuda.fp8_scales(sc.gathered(group, plan.rank, plan.world, plan.kv_rows)):
+                return cp_forward(plan, q, k, v, scale, group, transport, heads_k_stride)
     if _fused_ok(q, k, group, plan):
         from . import fused
 

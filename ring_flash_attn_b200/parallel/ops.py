@@ -154,25 +154,50 @@ def _out_dtype(q: Tensor) -> torch.dtype:
     return torch.bfloat16 if q.element_size() == 1 else q.dtype  # fp8 inputs produce bf16 outputs
 
 
+def _fp8_kernel_takes(plan, q: Tensor, k: Tensor, kv_block: int) -> bool:
+    """The fp8 forward kernel (e4m3, head_dim 128, Blackwell GPU) reads one K and one V descale per 128-key tile:
+    descale blocks must be whole tiles (multiples of 128 rows, with every key segment starting on a tile boundary)
+    or cover the whole local shard; windows are not instantiated for fp8.  ``RFA_B200_FP8_KERNEL=0`` disables it."""
+    import os
+
+    from ..ops import attn_cuda, cuda_ext
+
+    if os.environ.get("RFA_B200_FP8_KERNEL", "2") == "0" or not attn_cuda.is_fp8_kernel_input(q, k):
+        return False
+    if not cuda_ext.available_for(q) or engine.plan_has_window(plan):
+        return False
+    return kv_block == k.shape[0] or (kv_block % 128 == 0 and all(s.kv_row0 % 128 == 0 for s in plan.segments))
+
+
 @torch.library.custom_op("rfa_b200::cp_attn_fwd", mutates_args=())
 def cp_attn_fwd(q: Tensor, k: Tensor, v: Tensor, cu_a: Optional[Tensor], cu_b: Optional[Tensor],
-                scale_qk: Optional[Tensor], scale_v: Optional[Tensor], scheme: str, group: str, spec: List[int],
-                softmax_scale: float, deterministic: bool) -> Tuple[Tensor, Tensor]:
+                scale_q: Optional[Tensor], scale_k: Optional[Tensor], scale_v: Optional[Tensor], scheme: str,
+                group: str, spec: List[int], softmax_scale: float, deterministic: bool) -> Tuple[Tensor, Tensor]:
     """q (T, Hq, D), k / v (T, Hkv, D) token-major -> (out (T, Hq, D), lse (Hq, T) fp32).
 
-    ``scale_qk`` / ``scale_v``: per-head descales of the fp8 forward kernel (None for bf16 / fp16)."""
+    ``scale_q`` (nq, Hq) / ``scale_k``, ``scale_v`` (nk, Hkv): block descale tables of fp8 q / k / v (None for
+    bf16 / fp16): one fp32 per block of T / nq (T / nk) consecutive token-major rows and head."""
     pg = resolve_group(group)
     plan, transport, stride = resolve_plan(scheme, spec, cu_a, cu_b, q.shape[0], pg)
-    if scale_qk is not None:
+    if scale_q is not None:
         from ..ops import attn_cuda
 
-        with attn_cuda.fp8_scales(scale_qk, scale_v):
-            return engine.cp_forward(plan, q, k, v, softmax_scale, pg, transport, stride)
+        q_block, kv_block = -(-q.shape[0] // scale_q.shape[0]), -(-k.shape[0] // scale_k.shape[0])
+        if _fp8_kernel_takes(plan, q, k, kv_block):
+            sc = attn_cuda.Fp8Scales(scale_q.float().contiguous(), q_block, scale_k.float().contiguous(),
+                                     scale_v.float().contiguous(), kv_block)
+            with attn_cuda.fp8_scales(sc):
+                return engine.cp_forward(plan, q, k, v, softmax_scale, pg, transport, stride)
+        # key tiles would straddle descale blocks (or no kernel for this input): expand to bf16 in front of the op
+        def deq(x, table, block):
+            return (x.float() * table.float().repeat_interleave(block, dim=0)[:x.shape[0]].unsqueeze(-1)).to(torch.bfloat16)
+
+        q, k, v = deq(q, scale_q, q_block), deq(k, scale_k, kv_block), deq(v, scale_v, kv_block)
     return engine.cp_forward(plan, q, k, v, softmax_scale, pg, transport, stride)
 
 
 @cp_attn_fwd.register_fake
-def _(q, k, v, cu_a, cu_b, scale_qk, scale_v, scheme, group, spec, softmax_scale, deterministic):
+def _(q, k, v, cu_a, cu_b, scale_q, scale_k, scale_v, scheme, group, spec, softmax_scale, deterministic):
     return (q.new_empty(q.shape, dtype=_out_dtype(q)), q.new_empty((q.shape[1], q.shape[0]), dtype=torch.float32))
 
 
@@ -191,7 +216,7 @@ def _(dout, q, k, v, out, lse, cu_a, cu_b, scheme, group, spec, softmax_scale, d
 
 
 def _setup_context(ctx, inputs, output):
-    q, k, v, cu_a, cu_b, _sqk, _sv, scheme, group, spec, softmax_scale, deterministic = inputs
+    q, k, v, cu_a, cu_b, _sq, _sk, _sv, scheme, group, spec, softmax_scale, deterministic = inputs
     out, lse = output
     ctx.save_for_backward(q, k, v, out, lse, cu_a, cu_b)
     ctx.meta = (scheme, group, list(spec), softmax_scale, deterministic)
@@ -204,7 +229,7 @@ def _backward(ctx, dout, _dlse):
     if dout is None:
         dout = torch.zeros_like(out)
     dq, dk, dv = cp_attn_bwd(dout, q, k, v, out, lse, cu_a, cu_b, scheme, group, spec, softmax_scale, deterministic)
-    return dq, dk, dv, None, None, None, None, None, None, None, None, None
+    return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
 
 
 torch.library.register_autograd("rfa_b200::cp_attn_fwd", _backward, setup_context=_setup_context)

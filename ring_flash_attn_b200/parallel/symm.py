@@ -82,6 +82,9 @@ class PeerContext:
         self.stage_half = 0
         self.inbox: Optional[PeerBuffer] = None
         self.n_push_ctas = int(os.environ.get("RFA_B200_PUSH_CTAS", "24"))
+        # copy-engine K/V transport (csrc/peer_mem.cpp:kv_push_dma): a side stream + a ring of epoch words
+        self.side: Optional[torch.cuda.Stream] = None
+        self.flag_host = self.flag_dev = None
 
     # -- buffers ------------------------------------------------------------------------------------
     def _quiesce(self):
@@ -132,6 +135,34 @@ class PeerContext:
         self.sent_cum, self.dkv_cum = list(sent), list(dkv)
 
     # -- per-call context object --------------------------------------------------------------------
+    def kv_transport(self, plan: CPPlan) -> str:
+        """``push``: communication CTAs inside the attention launch (TMA bulk copies over NVLink).  ``dma``: the copy
+        engines move the rows on a side stream while the launch (without push CTAs) waits on the same flags.
+        ``RFA_B200_KV_TRANSPORT`` selects; llama3 plans (needs only known on the device) always push."""
+        mode = os.environ.get("RFA_B200_KV_TRANSPORT", "push")
+        if mode != "dma" or is_dynamic(plan) or not cuda_ext.load().dma_transport_available():
+            return "push"
+        return "dma"
+
+    def push_dma(self, plan: CPPlan, k: torch.Tensor, v: torch.Tensor, fc) -> torch.cuda.Event:
+        """Queue this call's K/V rows for every peer on the side stream; returns the event that marks them sent."""
+        C = cuda_ext.load()
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.device)
+            self.flag_host = torch.zeros(1024, dtype=torch.int32).pin_memory()
+            self.flag_dev = torch.zeros(1024, dtype=torch.int32, device=self.device)
+        tasks = push_tasks_host(plan, self, int(fc.row_bytes))
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)  # K / V are produced on the main stream
+        self.side.wait_event(ready)
+        C.kv_push_dma(k, v, tasks, list(self.stage.ptrs), list(self.pad.ptrs), int(self.pad.local_ptr),
+                      int(fc.parity_off), int(fc.row_bytes), self.rank, int(fc.epoch), self.flag_host, self.flag_dev,
+                      self.side.cuda_stream)
+        sent = torch.cuda.Event()
+        sent.record(self.side)
+        return sent
+
     def fused_ctx(self, plan: CPPlan, k: torch.Tensor, n_compute_ctas: int, dyn_needs: Optional[torch.Tensor] = None):
         C = cuda_ext.load()
         rows, hkv, d = plan.kv_rows, k.shape[1], k.shape[2]
@@ -146,7 +177,10 @@ class PeerContext:
         fc.v_stage = self.stage.tensor(half + region, (self.world * rows, hkv, d), k.dtype)
         fc.my_pad = self.pad_tensor
         fc.rows_cap, fc.region_bytes = rows, region
-        if dyn_needs is None:
+        if dyn_needs is None and self.kv_transport(plan) == "dma":
+            # the copy engines push (push_dma); the launch has no communication CTAs
+            tasks, per_dst, n_tasks = torch.zeros((0, 4), dtype=torch.int64, device=k.device), [0] * self.world, 0
+        elif dyn_needs is None:
             tasks, per_dst = push_tasks(plan, self, row_bytes, k.device)
             n_tasks = int(tasks.shape[0])
         else:
@@ -305,6 +339,25 @@ def _ranges(plan: CPPlan, src: int) -> List[Tuple[int, int]]:
     return out
 
 
+def push_tasks_host(plan: CPPlan, ctx: PeerContext, row_bytes: int) -> torch.Tensor:
+    """The push table as a CPU tensor with ONE task per (destination, range, K|V) - the copy engines take whole
+    ranges, chunking only matters for spreading work over push CTAs."""
+    key = ("push_host", row_bytes)
+    cache = attn_cuda._cache(plan)
+    if key not in cache:
+        needs = needs_matrix(plan, ctx.group)
+        me, world, rows = plan.rank, plan.world, plan.kv_rows
+        region = world * rows * row_bytes
+        table = []
+        for step in range(1, world):
+            dst = (me + step) % world
+            for lo, hi in needs[dst][me]:
+                for which in (0, 1):
+                    table.append([lo, which * region + (me * rows + lo) * row_bytes, (hi - lo) | (dst << 32), which])
+        cache[key] = torch.tensor(table, dtype=torch.int64) if table else torch.zeros((0, 4), dtype=torch.int64)
+    return cache[key]
+
+
 def push_tasks(plan: CPPlan, ctx: PeerContext, row_bytes: int, device):
     """(int64 task table on the device, tasks per destination).  Cached on the plan."""
     key = ("push", row_bytes, device.index)
@@ -368,11 +421,14 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
     if not covered:
         lse.fill_(float("-inf"))
     snap = ctx.snapshot()
+    sent = None
     try:
         fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hq, dyn)
+        if dyn is None and ctx.kv_transport(plan) == "dma":
+            sent = ctx.push_dma(plan, k, v, fc)
         if attn_cuda.is_fp8_kernel_input(q, k):
-            sq, sv = attn_cuda.current_fp8_scales()
-            C.attn_fwd_fused_fp8(attn_cuda._rows3(q), k, v, items, segs, sq, sv, out, lse, tq, float(scale), fc)
+            sc = attn_cuda.current_fp8_scales()  # tables of every rank's shard (engine.cp_forward gathered them)
+            C.attn_fwd_fused_fp8(attn_cuda._rows3(q), k, v, items, segs, *sc.args(), out, lse, tq, float(scale), fc)
         elif window:
             C.attn_fwd_fused_window(attn_cuda._rows3(q), k, v, items, segs, seg_lo, out, lse, tq, float(scale), fc)
         else:
@@ -380,6 +436,8 @@ def fused_forward(plan: CPPlan, q, k, v, scale, group):
     except Exception:
         ctx.restore(snap)  # nothing reached the device: keep host and device counters in step
         raise
+    if sent is not None:
+        torch.cuda.current_stream(q.device).wait_event(sent)  # k / v stay alive until the copy engines are done
     cuda_ext.note_launch()
     return out, lse
 
@@ -438,8 +496,11 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     dq = attn_cuda.dq_workspace.acquire(q)  # zeroed fp32 accumulator, re-zeroed by dq_finalize
     dyn = needs_gathered(plan, ctx, q.device) if is_dynamic(plan) else None
     snap = ctx.snapshot()
+    sent = None
     try:
         fc = ctx.fused_ctx(plan, k, int(items.shape[0]) * hkv, dyn)
+        if dyn is None and ctx.kv_transport(plan) == "dma":
+            sent = ctx.push_dma(plan, k, v, fc)
         me, esize = plan.rank, k.element_size()
         fc.dk_ptrs = [p + me * ctx.inbox_slot_stride * esize for p in ctx.inbox.ptrs]
         fc.dv_ptrs = [p + (me * ctx.inbox_slot_stride + ctx.inbox_kv_stride) * esize for p in ctx.inbox.ptrs]
@@ -453,6 +514,8 @@ def fused_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, determin
     except Exception:
         ctx.restore(snap)  # nothing reached the device: keep host and device counters in step
         raise
+    if sent is not None:
+        torch.cuda.current_stream(q.device).wait_event(sent)
     cuda_ext.note_launch()
     # owner-side reduction of the inbox (waits for the peers' "gradients landed" epochs on the device)
     tasks = reduce_tasks(plan, ctx, q.device)

@@ -66,11 +66,20 @@ class FakeExt:
         assert seg_lo.numel() == segs.shape[0]
         self._fwd(q, k, v, items, segs, seg_lo.tolist(), out, lse, scale)
 
-    def attn_fwd_fp8(self, q, k, v, items, segs, sqk, sv, out, lse, lse_S, scale):
+    def attn_fwd_fp8(self, q, k, v, items, segs, q_scale, q_block, k_scale, v_scale, kv_block, v_ref, kv_row0, out, lse,
+                     lse_S, scale):
+        """Contract of the block-scaled fp8 forward: dequantise with the tables, then the plain forward."""
         self.calls.append("attn_fwd_fp8")
         assert q.dtype == torch.float8_e4m3fn and out.dtype == torch.bfloat16
-        assert sqk.numel() == q.shape[1] and sv.numel() == k.shape[1]
-        self._fwd(q, k, v, items, segs, None, out, lse, scale, sqk.float(), sv.float())
+        assert q_scale.shape[1] == q.shape[1] and k_scale.shape[1] == k.shape[1] == v_scale.shape[1]
+        assert torch.allclose(v_ref, v_scale.amax(dim=0)) or v_ref.numel() == k.shape[1]
+
+        def deq(x, table, block, row0=0):
+            rows = torch.arange(x.shape[0]) + row0
+            return x.float() * table[rows // block].unsqueeze(-1)
+
+        self._fwd(deq(q, q_scale, q_block), deq(k, k_scale, kv_block, kv_row0), deq(v, v_scale, kv_block, kv_row0),
+                  items, segs, None, out, lse, scale)
 
     # ------------------------------------------------------------------ backward
     def attn_bwd_delta(self, out, dout, delta, lse_S):

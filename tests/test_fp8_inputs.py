@@ -81,13 +81,20 @@ def test_fp8_kernel_opt_in_is_ignored_off_gpu(monkeypatch):
     ref, _ = attention_oracle(deq[:, :, 0], deq[:, :, 1], deq[:, :, 2], True)
     out = rfa.ring_flash_attn_qkvpacked_func(q8, causal=True, descale=d)
     torch.testing.assert_close(out.float(), ref, atol=3e-2, rtol=3e-2)
-    # per-head reduction of descales (what the kernel path consumes)
-    x = torch.zeros(1, 8, 4, 128)
-    assert api._per_head(None, x).tolist() == [1.0] * 4
-    assert api._per_head(0.5, x).tolist() == [0.5] * 4
-    assert api._per_head(torch.tensor(2.0), x).tolist() == [2.0] * 4
-    assert api._per_head(torch.arange(4.0).view(1, 1, 4, 1), x).tolist() == [0.0, 1.0, 2.0, 3.0]
-    assert api._per_head(torch.ones(1, 2, 4, 1), x) is None  # token-block scales: not per-head
+    # canonical (blocks, heads) descale tables (what the kernel path consumes)
+    x = torch.zeros(2, 8, 4, 128)
+    assert api._scale_table(None, x).tolist() == [[1.0] * 4]
+    assert api._scale_table(0.5, x).tolist() == [[0.5] * 4]
+    assert api._scale_table(torch.tensor(2.0), x).tolist() == [[2.0] * 4]
+    assert api._scale_table(torch.arange(4.0).view(1, 1, 4, 1), x).tolist() == [[0.0, 1.0, 2.0, 3.0]]
+    blk = api._scale_table(torch.arange(16.0).view(2, 2, 4, 1), x)  # 4-token blocks x head, per batch element
+    assert blk.shape == (4, 4) and blk[1].tolist() == [4.0, 5.0, 6.0, 7.0] and blk[2].tolist() == [8.0, 9.0, 10.0, 11.0]
+    shared = api._scale_table(torch.arange(2.0).view(1, 2, 1, 1), x)  # the same token-block scales for every batch / head
+    assert shared.shape == (4, 4) and shared[:, 0].tolist() == [0.0, 1.0, 0.0, 1.0]
+    assert api._scale_table(torch.ones(2, 8, 4, 4), x) is None  # scales along head_dim (MX style): dequantise path
+    assert api._scale_table(torch.ones(1, 3, 4, 1), x) is None  # does not tile the tokens
+    packed = torch.zeros(12, 4, 128)
+    assert api._scale_table(torch.arange(12.0).view(3, 4, 1), packed).shape == (3, 4)
 
 
 def test_quantize_per_head_shapes_and_roundtrip():
@@ -102,7 +109,7 @@ def test_quantize_per_head_shapes_and_roundtrip():
     assert dq.shape == (1, 1, 4, 1) and dkv.shape == (1, 1, 2, 2, 1)
     assert (fp8.dequantize(q8, dq, torch.float32) - q).abs().max() < 0.07 * q.abs().max()
     # exactly the granularity the kernel path accepts
-    assert api._per_head(dq, q8) is not None
+    assert api._scale_table(dq, q8).shape == (1, 4)
     dk, dv = api._split_descale(dkv, 2, 2)
-    assert api._per_head(dk, kv8[:, :, 0]) is not None and api._per_head(dv, kv8[:, :, 1]) is not None
+    assert api._scale_table(dk, kv8[:, :, 0]).shape == (1, 2) and api._scale_table(dv, kv8[:, :, 1]).shape == (1, 2)
 

@@ -370,3 +370,29 @@ def test_head_dim_64_native(window):
     torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=2e-3)
     assert (q.grad.float() - rq.grad).abs().max().item() < 5e-2 * rq.grad.abs().max().item() + 2e-2
     assert (kv.grad.float() - rkv.grad).abs().max().item() < 5e-2 * rkv.grad.abs().max().item() + 2e-2
+
+
+@pytest.mark.parametrize("q_block,kv_block", [(128, 128), (1, 256), (64, 128)])
+def test_fp8_forward_block_scaled(q_block, kv_block):
+    """Block-scaled e4m3 inputs (BASELINE.json config 5): one descale per token block x head for q, per 128-key
+    tile (or a multiple) x kv head for k and v, applied INSIDE the forward kernel (fp32 scores / folded into P)."""
+    from ring_flash_attn_b200.ops import cuda_ext
+    from ring_flash_attn_b200.utils import fp8
+
+    torch.manual_seed(0)
+    B, S, H, HK = 2, 1024, 8, 2
+    # token-dependent magnitudes, so that block scales actually differ
+    amp = (1.0 + 3.0 * torch.rand(B, S, 1, 1, device="cuda"))
+    q = torch.randn(B, S, H, 128, device="cuda") * amp
+    kv = torch.randn(B, S, 2, HK, 128, device="cuda") * amp.unsqueeze(2)
+    q8, dq = fp8.quantize_blockwise(q, [1, q_block, 1, 0])
+    kv8, dkv = fp8.quantize_blockwise(kv, [1, kv_block, 1, 1, 0])
+    qd, kvd = fp8.dequantize(q8, dq, torch.float32), fp8.dequantize(kv8, dkv, torch.float32)
+    ref, ref_lse = attention_oracle(qd, kvd[:, :, 0], kvd[:, :, 1], True)
+    before = cuda_ext.launch_counter().value
+    out, lse, _ = rfa.zigzag_ring_flash_attn_kvpacked_func(q8, kv8, causal=True, descale=(dq, dkv),
+                                                           return_attn_probs=True)
+    assert cuda_ext.launch_counter().value == before + 1 and out.dtype == torch.bfloat16, "not the fp8 kernel"
+    torch.testing.assert_close(lse, ref_lse, atol=2e-2, rtol=2e-2)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-2 * ref.abs().max().item() + 2e-2, err

@@ -309,3 +309,39 @@ def test_llama3_head_groups_2gpu():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     run_distributed(_llama3_strict_groups, 2, backend="nccl")
+
+
+def _fp8_block_scaled_fused(rank, world):
+    """stripe attention on block-scaled e4m3 shards through the fused launch: e4m3 K/V rows on the NVLink wire, the
+    sources' descale tables gathered on the device."""
+    from ring_flash_attn_b200.ops import cuda_ext
+    from ring_flash_attn_b200.utils import fp8
+
+    os.environ["RFA_B200_DISABLE_P2P"] = "0"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(5)
+    B, S, H = 2, 1024 * world, 4
+    qkv = torch.randn(B, S, 3, H, 128, device=dev) * (1.0 + 3.0 * torch.rand(B, S, 1, 1, 1, device=dev))
+    dist.broadcast(qkv, src=0)
+    local = layouts.shard_stripe(qkv, rank, world)
+    q8, scale = fp8.quantize_blockwise(local, [1, 128, 1, 1, 0])
+    deq = fp8.dequantize(q8, scale, torch.float32)
+    parts = [torch.empty_like(deq) for _ in range(world)]
+    dist.all_gather(parts, deq)
+    full = layouts.unshard("stripe", parts)
+    ref, ref_lse = attention_oracle(full[:, :, 0], full[:, :, 1], full[:, :, 2], True)
+    for _ in range(2):
+        before = cuda_ext.launch_counter().value
+        out, lse, _ = rfa.stripe_flash_attn_qkvpacked_func(q8, causal=True, descale=scale, return_attn_probs=True)
+        torch.cuda.synchronize()
+        assert cuda_ext.launch_counter().value == before + 1, "block-scaled fp8 did not take the fused fp8 launch"
+        want = layouts.shard_stripe(ref, rank, world)
+        err = (out.float() - want).abs().max().item()
+        assert err < 6e-2 * want.abs().max().item() + 2e-2, err
+        torch.testing.assert_close(lse, layouts.shard_stripe(ref_lse, rank, world, dim=2), atol=2e-2, rtol=2e-2)
+
+
+def test_fp8_block_scaled_fused_2gpu():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_fp8_block_scaled_fused, 2, backend="nccl")

@@ -120,6 +120,30 @@ def _fp8_case(rank, world):
         assert out.dtype == torch.bfloat16
         torch.testing.assert_close(out.float(), shard(ref, rank, world), **BF16)
         torch.testing.assert_close(lse, shard(ref_lse, rank, world, dim=2), atol=2e-3, rtol=2e-3)
+    # block-scaled: one descale per 128 LOCAL tokens and head (BASELINE.json config 5).  The shard is quantised
+    # locally (what a training step does with its activations), so every rank has different K / V tables and the
+    # transports have to bring the source's table along with its rows.
+    for scheme, fn in (("ring", rfa.ring_flash_attn_kvpacked_func), ("stripe", rfa.stripe_flash_attn_kvpacked_func)):
+        shard = getattr(layouts, f"shard_{scheme}")
+        lq8, ldq = fp8.quantize_blockwise(shard(q, rank, world), [1, 128, 1, 0])
+        lkv8, ldkv = fp8.quantize_blockwise(shard(kv, rank, world), [1, 128, 1, 1, 0])
+        parts_q = [torch.empty_like(lq8.view(torch.uint8)) for _ in range(world)]
+        deq_q, deq_kv = fp8.dequantize(lq8, ldq, torch.float32), fp8.dequantize(lkv8, ldkv, torch.float32)
+        if world > 1:
+            gq = [torch.empty_like(deq_q) for _ in range(world)]
+            gkv = [torch.empty_like(deq_kv) for _ in range(world)]
+            dist.all_gather(gq, deq_q)
+            dist.all_gather(gkv, deq_kv)
+        else:
+            gq, gkv = [deq_q], [deq_kv]
+        fq, fkv = layouts.unshard(scheme, gq), layouts.unshard(scheme, gkv)
+        ref_b, ref_lse_b = attention_oracle(fq, fkv[:, :, 0], fkv[:, :, 1], True)
+        fake.calls.clear()
+        out, lse, _ = fn(lq8, lkv8, causal=True, descale=(ldq, ldkv), return_attn_probs=True)
+        assert set(fake.calls) == {"attn_fwd_fp8"}, fake.calls
+        torch.testing.assert_close(out.float(), shard(ref_b, rank, world), **BF16)
+        torch.testing.assert_close(lse, shard(ref_lse_b, rank, world, dim=2), atol=2e-3, rtol=2e-3)
+        del parts_q
     # llama3 entry point: the all-gather transport slices the descales per head group
     cu = torch.tensor([0, S // 2 + 3, S], dtype=torch.int32)
     refv, _ = varlen_attention_oracle(qd[0], kvd[0, :, 0], kvd[0, :, 1], cu, True)
