@@ -146,11 +146,13 @@ def main():
     from ring_flash_attn_b200.parallel.symm import _ranges
 
     def link_bytes(plan, hkv, batch=1):
-        """NVLink bytes of the busiest rank: K/V rows of other shards this rank's queries can see (bf16, fetched in
-        the forward and again in the backward) plus the fp32 dK/dV partials it returns for the same rows."""
+        """NVLink bytes of the busiest rank, per direction: K/V rows of other shards this rank's queries can see (model
+        dtype, received in the forward and again in the backward) plus the dK/dV partials for the same rows (model
+        dtype since round 2; round 1 and the reference send fp32, i.e. twice these bytes).  The links are full duplex:
+        what a rank receives (K/V in, dK/dV of its own shard in) and what it sends are of the same size."""
         rows = sum(hi - lo for src in range(world) if src != rank for lo, hi in _ranges(plan, src))
         kv = rows * hkv * d * 2 * 2
-        total = kv * (1 if fwd else 2) + (0 if fwd else rows * hkv * d * 2 * 4)
+        total = kv * (1 if fwd else 2) + (0 if fwd else kv)
         t = torch.tensor([float(total)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])

@@ -48,6 +48,12 @@ section("Layouts (`ring_flash_attn_b200.parallel.layouts`) *(extension)*")
 for n, o in inspect.getmembers(layouts, inspect.isfunction):
     if not n.startswith("_") and o.__module__ == layouts.__name__:
         entry(n, o, ext=True)
+section("Verification and the op boundary *(extension)*")
+from ring_flash_attn_b200.parallel import ops  # noqa: E402
+from ring_flash_attn_b200.utils import verify  # noqa: E402
+
+entry("ring_flash_attn_b200.utils.verify.sampled_check", verify.sampled_check, ext=True)
+lines += ["### `torch.ops.rfa_b200.cp_attn_fwd` / `cp_attn_bwd` *(extension)*", "", inspect.getdoc(ops), ""]
 with open(os.path.join(ROOT, "docs", "API.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
 print("wrote docs/API.md:", len(lines), "lines")

@@ -63,5 +63,5 @@ def test_varlen_and_llama3_fullgraph():
 def test_op_is_registered_with_fake_and_autograd():
     op = torch.ops.rfa_b200.cp_attn_fwd.default
     q = torch.randn(8, 2, 16)
-    torch.library.opcheck(op, (q, q.clone(), q.clone(), None, None, None, None, "ring", "", [1, 8, 1, -1, -1],
+    torch.library.opcheck(op, (q, q.clone(), q.clone(), None, None, None, None, None, "ring", "", [1, 8, 1, -1, -1],
                                0.25, False), test_utils=("test_schema", "test_faketensor"))
