@@ -347,12 +347,16 @@ class _DqWorkspace:
         stream = torch.cuda.current_stream(q.device).cuda_stream if q.is_cuda else 0
         return (str(q.device), stream, q.numel())
 
+    MAX_BYTES = 2 << 30  # total fp32 workspace kept alive across calls (beyond it the oldest shapes are dropped)
+
     def acquire(self, q: torch.Tensor) -> torch.Tensor:
         key = self._key(q)
         ent = self._bufs.get(key)
         if ent is None:
-            if len(self._bufs) >= 8:  # a handful of live shapes; drop the oldest
-                self._bufs.pop(next(iter(self._bufs)))
+            need = 4 * q.numel()
+            while self._bufs and (len(self._bufs) >= 8 or
+                                  need + sum(4 * e[0].numel() for e in self._bufs.values()) > self.MAX_BYTES):
+                self._bufs.pop(next(iter(self._bufs)))  # a handful of live shapes; drop the oldest
             ent = [torch.zeros(q.numel(), dtype=torch.float32, device=q.device), False]
             self._bufs[key] = ent
         elif ent[1]:  # a previous backward died between launch and finalize: do not trust the contents

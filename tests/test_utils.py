@@ -91,3 +91,51 @@ def test_get_default_args_returns_fresh_dict():
     assert utils.get_default_args(f)["b"] == 2
     assert set(utils.__all__) >= {"update_out_and_lse", "RingComm", "AllGatherComm", "flatten_varlen_lse",
                                   "unflatten_varlen_lse", "get_default_args"}
+
+
+def test_fused_heads_per_pass_budget(monkeypatch):
+    """llama3 on the fused path: heads_k_stride is the granularity, RFA_B200_STAGE_BUDGET_MB the cap of one launch."""
+    import torch
+
+    from ring_flash_attn_b200.ops.plan import CPPlan
+    from ring_flash_attn_b200.parallel import engine
+
+    plan = CPPlan(world=8, rank=0, q_rows=8192, kv_rows=8192)
+    k = torch.empty(8192, 8, 128, dtype=torch.bfloat16)
+    per_head_mb = 2 * 2 * 8 * 8192 * 128 * 2 / 2 ** 20  # 64 MiB of staging per kv head
+    assert per_head_mb == 64
+    monkeypatch.delenv("RFA_B200_LLAMA3_HEAD_GROUPS", raising=False)
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "8192")
+    assert engine.fused_heads_per_pass(plan, k, 1) == 8  # everything fits: one launch over all heads
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "300")
+    assert engine.fused_heads_per_pass(plan, k, 1) == 4  # largest divisor of 8 whose staging fits 300 MiB
+    assert engine.fused_heads_per_pass(plan, k, 4) == 4
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "1")
+    assert engine.fused_heads_per_pass(plan, k, 2) == 2  # never below the caller's stride
+    monkeypatch.setenv("RFA_B200_LLAMA3_HEAD_GROUPS", "strict")
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "8192")
+    assert engine.fused_heads_per_pass(plan, k, 2) == 2  # the reference's memory behaviour
+    import pytest
+
+    with pytest.raises(ValueError):
+        engine.fused_heads_per_pass(plan, k, 3)
+
+
+def test_fp8_scale_tables_follow_rows():
+    """Fp8Scales: per-source views and head slices index the gathered tables like the staging buffer."""
+    import torch
+
+    from ring_flash_attn_b200.ops.attn_cuda import Fp8Scales
+
+    q = torch.arange(8.0).view(4, 2)            # 4 query blocks x 2 heads
+    k = torch.arange(6.0).view(3, 2) + 1.0      # 3 key blocks of 128 rows x 2 kv heads
+    v = torch.tensor([[1.0, 5.0], [2.0, 4.0], [3.0, 3.0]])
+    sc = Fp8Scales(q, 96, k, v, 128)
+    assert sc.v_ref.tolist() == [3.0, 5.0] and sc.kv_row0 == 0 and sc.world_rows == 0
+    assert sc.gathered(None, 0, 1, 384) is sc    # world 1: nothing to gather
+    allr = Fp8Scales(q, 96, torch.cat([k, k + 10]), torch.cat([v, v]), 128, sc.v_ref, world_rows=384, kv_row0=384)
+    src0 = allr.for_source(0)
+    assert src0.kv_row0 == 0 and src0.k is allr.k
+    h = allr.heads(slice(1, 2), slice(1, 2))
+    assert h.q.shape == (4, 1) and h.k.shape == (6, 1) and h.v_ref.tolist() == [5.0] and h.kv_row0 == 384
+    assert len(allr.args()) == 7
