@@ -1,8 +1,9 @@
 """torch.distributed transports used by the fallback (CPU/gloo, or GPUs without peer access).
 
 Capability parity with the reference's ``RingComm`` and ``AllGatherComm``
-(/root/reference/ring_flash_attn/utils.py:98-168).  The fused sm_100a path does not use these: it
-pulls K/V straight out of the owner's memory over NVLink (``parallel/symm.py``).
+(/root/reference/ring_flash_attn/utils.py:98-168).  The fused sm_100a path does not use these: the
+attention kernels' own communication CTAs push K/V rows into the peers' memory over NVLink
+(``parallel/symm.py``, ``csrc/comm_device.cuh``).
 """
 from __future__ import annotations
 

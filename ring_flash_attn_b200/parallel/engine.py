@@ -61,7 +61,10 @@ def _kernels_take(plan: CPPlan) -> bool:
         return True
     from ..ops import attn_cuda
 
-    return attn_cuda.window_kernels_enabled()
+    if attn_cuda.window_kernels_enabled():
+        return True
+    _warn_once("RFA_B200_WINDOW_KERNEL=0: sliding-window plans run on the dense torch blocks (slow)")
+    return False
 
 
 def _dense_tiles(row0: int, n_rows: int, s: Segment):

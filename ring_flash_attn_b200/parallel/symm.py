@@ -102,6 +102,9 @@ class PeerContext:
         self._quiesce()
         if self.stage is not None:
             self.stage.close()
+            # growing is collective (barrier + cudaMalloc + IPC exchange): over-allocate by a quarter when it has
+            # to happen again, so that a stream of slowly growing packed batches does not stall every few steps
+            need_half = max(need_half, self.stage_half + self.stage_half // 4)
         self.stage_half = (need_half + 4095) // 4096 * 4096
         self.stage = PeerBuffer(2 * self.stage_half, self.device, self.group)
         self._quiesce()
@@ -116,6 +119,7 @@ class PeerContext:
         self._quiesce()
         if self.inbox is not None:
             self.inbox.close()
+            need = max(need, self.inbox.nbytes + self.inbox.nbytes // 4)  # see ensure_stage
         self.inbox = PeerBuffer(need, self.device, self.group)
         self._quiesce()
 

@@ -71,7 +71,7 @@ def sampled_check(scheme: str, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor
     tol: Dict[str, float] = {}
 
     def note(name, got, ref, rel):
-        ref = ref.float()
+        got, ref = got.detach(), ref.detach().float()
         err[name] = float((got.float() - ref).abs().max())
         finite = ref[torch.isfinite(ref)]
         tol[name] = rel * float(finite.abs().max() if finite.numel() else 1.0) + 2e-3
