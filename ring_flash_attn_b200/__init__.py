@@ -7,7 +7,7 @@ The Hugging Face adapter is imported lazily so that ``import ring_flash_attn_b20
 from .parallel.api import *  # noqa: F401,F403
 from .parallel.api import __all__ as _api_all
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 _LAZY = {
     "substitute_hf_flash_attn": ("ring_flash_attn_b200.models.hf_adapter", "substitute_hf_flash_attn"),
