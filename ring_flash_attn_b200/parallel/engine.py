@@ -334,21 +334,22 @@ def _warn_once(msg: str) -> None:
         warnings.warn("ring_flash_attn_b200: " + msg, RuntimeWarning, stacklevel=3)
 
 
-def fused_heads_per_pass(plan: CPPlan, k: torch.Tensor, heads_k_stride: int) -> int:
-    """How many kv heads one fused launch of the llama3 scheme covers.
+def fused_heads_per_pass(plan: CPPlan, k: torch.Tensor, heads_k_stride: int, strict_env: bool = True) -> int:
+    """How many kv heads one fused launch covers.
 
     The reference gathers ``heads_k_stride`` kv heads at a time so that the gathered K/V buffer stays bounded
-    (/root/reference/ring_flash_attn/llama3_flash_attn_varlen.py:89-115).  On the fused path the quantity that grows
-    with the number of heads is the peer-mapped staging buffer (every source's rows x heads, two call parities), so
-    ``heads_k_stride`` is the granularity and ``RFA_B200_STAGE_BUDGET_MB`` (default 8192) the cap: as many multiples of
-    ``heads_k_stride`` heads per launch as fit the budget - all of them when memory allows, because one launch over
-    all heads is the fastest schedule.  ``RFA_B200_LLAMA3_HEAD_GROUPS=strict`` uses exactly ``heads_k_stride`` heads
-    per launch (the reference's memory behaviour)."""
+    (/root/reference/ring_flash_attn/llama3_flash_attn_varlen.py:89-115), and its ring schemes hold one K/V shard in
+    flight (utils.py:117).  On the fused path the quantity that grows with the number of heads is the peer-mapped
+    staging buffer (every source's rows x heads, two call parities), so ``heads_k_stride`` is the granularity and
+    ``RFA_B200_STAGE_BUDGET_MB`` (default 8192) the cap: as many multiples of ``heads_k_stride`` heads per launch as
+    fit the budget - all of them when memory allows, because one launch over all heads is the fastest schedule.
+    ``RFA_B200_LLAMA3_HEAD_GROUPS=strict`` (llama3 only, ``strict_env``) uses exactly ``heads_k_stride`` heads per
+    launch (the reference's memory behaviour)."""
     hkv = k.shape[1]
     stride = max(1, min(int(heads_k_stride), hkv))
     if hkv % stride:
         raise ValueError(f"heads_k_stride={stride} must divide the number of kv heads ({hkv})")
-    if os.environ.get("RFA_B200_LLAMA3_HEAD_GROUPS", "auto") == "strict":
+    if strict_env and os.environ.get("RFA_B200_LLAMA3_HEAD_GROUPS", "auto") == "strict":
         return stride
     budget = int(os.environ.get("RFA_B200_STAGE_BUDGET_MB", "8192")) << 20
     per_head = 2 * 2 * plan.world * plan.kv_rows * k.shape[2] * k.element_size()  # parities x (K, V) x sources x rows
@@ -361,10 +362,17 @@ def fused_heads_per_pass(plan: CPPlan, k: torch.Tensor, heads_k_stride: int) -> 
 
 
 def _fused_by_head_groups(plan, k, heads_k_stride, transport):
-    """(heads per pass) when the fused llama3 path must run in several passes over kv-head groups, else None."""
-    if transport != "allgather" or plan.world == 1:
+    """(heads per pass) when the fused path must run in several passes over kv-head groups, else None.
+
+    llama3 (``allgather`` transport): granularity ``heads_k_stride``.  Ring / zigzag / stripe schemes: granularity
+    one kv head, only when the staging of all heads would exceed ``RFA_B200_STAGE_BUDGET_MB`` - per-GPU staging is
+    then O(S * g / Hkv) for g heads per pass instead of O(S)."""
+    if plan.world == 1:
         return None
-    g = fused_heads_per_pass(plan, k, heads_k_stride)
+    if transport == "allgather":
+        g = fused_heads_per_pass(plan, k, heads_k_stride)
+    else:
+        g = fused_heads_per_pass(plan, k, 1, strict_env=False)
     return g if g < k.shape[1] else None
 
 

@@ -311,6 +311,29 @@ def test_llama3_head_groups_2gpu():
     run_distributed(_llama3_strict_groups, 2, backend="nccl")
 
 
+def _ring_schemes_head_groups(rank, world):
+    """A staging budget smaller than one launch over all heads (RFA_B200_STAGE_BUDGET_MB=0): zigzag / ring / stripe
+    run one fused launch per kv head, like llama3's head-group passes."""
+    from ring_flash_attn_b200.ops import cuda_ext
+
+    os.environ["RFA_B200_STAGE_BUDGET_MB"] = "0"
+    try:
+        before = cuda_ext.launch_counter().value
+        _batch_case(rank, world, "zigzag", True, True, 4, 2, 512, 2)
+        # per call: (fwd + delta + bwd + reduce + dq_finalize) x 2 head groups
+        assert cuda_ext.launch_counter().value - before >= 2 * 2 * 4
+        _batch_case(rank, world, "stripe", True, True, 4, 4, 384, 1)
+        _batch_case(rank, world, "ring", False, True, 4, 2, 256, 1)
+    finally:
+        os.environ.pop("RFA_B200_STAGE_BUDGET_MB", None)
+
+
+def test_ring_schemes_head_groups_2gpu():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_ring_schemes_head_groups, 2, backend="nccl")
+
+
 def _fp8_block_scaled_fused(rank, world):
     """stripe attention on block-scaled e4m3 shards through the fused launch: e4m3 K/V rows on the NVLink wire, the
     sources' descale tables gathered on the device."""

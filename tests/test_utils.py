@@ -121,6 +121,27 @@ def test_fused_heads_per_pass_budget(monkeypatch):
         engine.fused_heads_per_pass(plan, k, 3)
 
 
+def test_ring_schemes_head_groups_under_budget(monkeypatch):
+    """zigzag / ring / stripe: all heads in one fused launch unless their staging exceeds the budget; then groups of
+    kv heads (granularity 1), never governed by the llama3-only strict switch."""
+    import torch
+
+    from ring_flash_attn_b200.ops.plan import CPPlan
+    from ring_flash_attn_b200.parallel import engine
+
+    plan = CPPlan(world=8, rank=0, q_rows=8192, kv_rows=8192)
+    k = torch.empty(8192, 8, 128, dtype=torch.bfloat16)  # 64 MiB of staging per kv head
+    monkeypatch.setenv("RFA_B200_LLAMA3_HEAD_GROUPS", "strict")
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "8192")
+    assert engine._fused_by_head_groups(plan, k, 1, "ring") is None
+    assert engine._fused_by_head_groups(plan, k, 1, "allgather") == 1
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "200")
+    assert engine._fused_by_head_groups(plan, k, 1, "ring") == 2
+    monkeypatch.setenv("RFA_B200_STAGE_BUDGET_MB", "0")
+    assert engine._fused_by_head_groups(plan, k, 1, "ring") == 1
+    assert engine._fused_by_head_groups(CPPlan(world=1, rank=0, q_rows=64, kv_rows=64), k, 1, "ring") is None
+
+
 def test_fp8_scale_tables_follow_rows():
     """Fp8Scales: per-source views and head slices index the gathered tables like the staging buffer."""
     import torch
