@@ -291,6 +291,40 @@ def bwd_covers_all_rows(items: List[List[int]], kv_rows: int) -> bool:
     return sum(it[1] for it in items) == kv_rows
 
 
+def ordered_dq_groups(items: List[List[int]], qsegs: List[List[int]]) -> Tuple[List[List[int]], List[int]]:
+    """Reorder a backward item table into LAUNCH GROUPS for a bitwise reproducible dQ.
+
+    A key-tile CTA adds its dQ^T partial tiles into the fp32 accumulator with unordered L2 reductions, so two key
+    tiles that reach the same query rows inside one launch make the rounding of dQ depend on timing.  Items of one
+    group reach pairwise disjoint query rows (all heads of an item run in the same launch: heads never share dQ
+    elements); the groups are launched one after the other on the stream, which fixes the order of the fp32 additions
+    of every dQ element to the group order.  Greedy first-fit in table order (heaviest tiles first).  Returns
+    (items in group order, group boundaries ``[0, n_0, n_0 + n_1, ...]``).
+
+    One causal sequence of T keys needs T / 128 groups (every key tile reaches the last query row), packed documents
+    run side by side.  This is the cost of ``deterministic=True`` (the reference forwards the flag to flash-attn's
+    backward, /root/reference/ring_flash_attn/ring_flash_attn.py:119, which serialises its dQ accumulation too)."""
+    groups: List[Tuple[List[int], List[Tuple[int, int]]]] = []  # (item indices, query-row intervals they reach)
+    for idx, it in enumerate(items):
+        spans = []
+        for q_row0, q_len, d, _lo in qsegs[it[2]:it[2] + it[3]]:
+            first = max(0, -d)  # first chunk row that sees key 0 of the tile
+            if first < q_len:
+                spans.append((q_row0 + first, q_row0 + q_len))
+        for members, taken in groups:
+            if all(a1 <= b0 or b1 <= a0 for a0, a1 in spans for b0, b1 in taken):
+                members.append(idx)
+                taken.extend(spans)
+                break
+        else:
+            groups.append(([idx], list(spans)))
+    order, bounds = [], [0]
+    for members, _ in groups:
+        order.extend(members)
+        bounds.append(len(order))
+    return [items[i] for i in order], bounds
+
+
 def bwd_tables_fused(plan: CPPlan, row_offset: Dict[int, int], device, flag_of_src: Dict[int, int]):
     """Backward tables for the fused multi-GPU launch: every key tile carries its owner rank and its row
     inside the owner's shard; tiles that no local query reaches are still emitted (they store zeros into
@@ -400,13 +434,19 @@ def fwd_tables(plan, segs, row_offset, device, key, flag_of_src=None):
     return c[k]
 
 
-def bwd_tables(plan, segs, row_offset, device, key, flag_of_src=None):
+def bwd_tables(plan, segs, row_offset, device, key, flag_of_src=None, ordered=False):
+    """(items, qsegs) device tables; ``ordered=True`` (deterministic dQ) returns (items, qsegs, group bounds) with the
+    items arranged in the launch groups of :func:`ordered_dq_groups`."""
     c = _cache(plan)
-    k = ("bwd", key, device.index)
+    k = ("bwd_ordered" if ordered else "bwd", key, device.index)
     if k not in c:
         items, qsegs = bwd_tables_host(plan, segs, row_offset, flag_of_src)
-        c[k] = (_to_dev(items, 8, device), _to_dev(qsegs, 4, device))
-        c[k + ("covered",)] = bwd_covers_all_rows(items, plan.kv_rows)
+        c[("bwd", key, device.index, "covered")] = bwd_covers_all_rows(items, plan.kv_rows)
+        if ordered:
+            items, bounds = ordered_dq_groups(items, qsegs)
+            c[k] = (_to_dev(items, 8, device), _to_dev(qsegs, 4, device), bounds)
+        else:
+            c[k] = (_to_dev(items, 8, device), _to_dev(qsegs, 4, device))
     return c[k]
 
 
@@ -488,30 +528,35 @@ def compute_delta(out, dout, hq_rows=None) -> torch.Tensor:
     return delta
 
 
-def backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq_accum, dk, dv):
+def backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq_accum, dk, dv, bounds=None, window=False):
+    """One backward launch over the item table, or one per launch group (``bounds`` from :func:`ordered_dq_groups`)."""
     C = cuda_ext.load()
-    if items.shape[0]:
-        C.attn_bwd(_rows3(q), _rows3(dout), _rows3(k), _rows3(v), dq_accum, items, qsegs, lse, delta, dk, dv,
-                   q.shape[0], float(scale))
+    launch = C.attn_bwd_window if window else C.attn_bwd
+    if not items.shape[0]:
+        return
+    args = (_rows3(q), _rows3(dout), _rows3(k), _rows3(v), dq_accum)
+    for a, b in ((0, items.shape[0]),) if bounds is None else zip(bounds[:-1], bounds[1:]):
+        launch(*args, items[a:b], qsegs, lse, delta, dk, dv, q.shape[0], float(scale))
         cuda_ext.note_launch()
 
 
 def segments_backward(plan: CPPlan, segs: Sequence[Segment], dout, q, k_src, v_src, lse, delta, scale, dq, dk, dv,
                       deterministic=False):
-    """Gradient contribution of ONE source shard: dq (fp32) accumulates, dk/dv (fp32, zeroed) are filled."""
+    """Gradient contribution of ONE source shard: dq (fp32) accumulates, dk/dv (fp32 or model dtype, zeroed) are
+    filled.  ``deterministic``: one launch per group of key tiles with disjoint query rows (ordered dQ additions)."""
     src = segs[0].src
+    lse, delta = lse.contiguous(), delta.contiguous()
     if has_window(segs):
-        C = cuda_ext.load()
         c = _cache(plan)
-        key = ("bwd_window", src, q.device.index)
+        key = ("bwd_window_ordered" if deterministic else "bwd_window", src, q.device.index)
         if key not in c:
             items, qsegs = bwd_tables_window_host(plan, segs, {src: 0})
-            c[key] = (_to_dev(items, 8, q.device), _to_dev(qsegs if qsegs else [[0, 0, 0, 0]], 4, q.device))
-        items, qsegs = c[key]
-        if items.shape[0]:
-            C.attn_bwd_window(_rows3(q), _rows3(dout), _rows3(k_src), _rows3(v_src), dq, items, qsegs,
-                              lse.contiguous(), delta.contiguous(), dk, dv, q.shape[0], float(scale))
-            cuda_ext.note_launch()
+            bounds = None
+            if deterministic:
+                items, bounds = ordered_dq_groups(items, qsegs)
+            c[key] = (_to_dev(items, 8, q.device), _to_dev(qsegs if qsegs else [[0, 0, 0, 0]], 4, q.device), bounds)
+        items, qsegs, bounds = c[key]
+        backward_launch(q, dout, k_src, v_src, lse, delta, items, qsegs, scale, dq, dk, dv, bounds, window=True)
         return
-    items, qsegs = bwd_tables(plan, segs, {src: 0}, q.device, ("step", src))
-    backward_launch(q, dout, k_src, v_src, lse.contiguous(), delta.contiguous(), items, qsegs, scale, dq, dk, dv)
+    items, qsegs, *rest = bwd_tables(plan, segs, {src: 0}, q.device, ("step", src), ordered=deterministic)
+    backward_launch(q, dout, k_src, v_src, lse, delta, items, qsegs, scale, dq, dk, dv, rest[0] if rest else None)

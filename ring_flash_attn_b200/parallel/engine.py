@@ -405,29 +405,46 @@ def cp_forward(plan: CPPlan, q, k, v, scale, group, transport="ring", heads_k_st
     return ring_forward(plan, q, k, v, scale, group)
 
 
+def deterministic_mode() -> str:
+    """``RFA_B200_DETERMINISTIC``: ``strict`` (default) - ``deterministic=True`` makes out / lse / dQ / dK / dV bitwise
+    reproducible; ``fast`` - keep the fastest schedule (dK / dV reproducible, dQ summed in no fixed order)."""
+    return os.environ.get("RFA_B200_DETERMINISTIC", "strict")
+
+
 def cp_backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, transport="ring",
                 heads_k_stride: int = 1, deterministic: bool = False):
-    if deterministic and _use_cuda_kernels(q, k) and _kernels_take(plan):
-        # the reference forwards the flag to flash-attn's backward (ring_flash_attn.py:119); here dK / dV have one
-        # writer per tile and a fixed-order owner-side sum, but dQ tiles are added with unordered fp32 L2 reductions
-        _warn_once("deterministic=True: dK / dV are bitwise reproducible on the sm_100a path, dQ is accumulated "
-                   "with fp32 reductions whose order is not fixed (run-to-run differences of ~1 ulp of fp32)")
-    if _fused_ok(q, k, group, plan):
+    # The reference forwards the flag to flash-attn's backward (ring_flash_attn.py:119).  On the sm_100a path out / lse
+    # never depend on timing, dK / dV have one writer per tile and a fixed-order owner-side sum; dQ tiles are added
+    # with unordered fp32 L2 reductions.  ``ordered``: launch the key tiles in groups with disjoint query rows
+    # (ops/attn_cuda.py:ordered_dq_groups) and, across GPUs, move K/V and dK/dV with the fixed-order ring /
+    # all-gather transports instead of the fused launch (whose key tiles of all sources share one launch).
+    kernels = _use_cuda_kernels(q, k) and _kernels_take(plan)
+    ordered = bool(deterministic) and kernels and deterministic_mode() != "fast"
+    if ordered:
+        _warn_once("deterministic=True: the backward runs one launch per group of key tiles with disjoint query rows"
+                   + (" and uses the torch.distributed transport instead of the fused NVLink path"
+                      if plan.world > 1 else "") +
+                   " (bitwise reproducible dQ / dK / dV, several times slower; RFA_B200_DETERMINISTIC=fast keeps "
+                   "the fast schedule with reproducible dK / dV and an unordered fp32 sum for dQ)")
+    elif deterministic and kernels:
+        _warn_once("deterministic=True with RFA_B200_DETERMINISTIC=fast: dK / dV are bitwise reproducible, dQ is "
+                   "accumulated with fp32 reductions whose order is not fixed (run-to-run differences of ~1 ulp of fp32)")
+    if _fused_ok(q, k, group, plan) and not (ordered and plan.world > 1):
         from . import fused
 
         g = _fused_by_head_groups(plan, k, heads_k_stride, transport)
         if g is None:
-            return fused.backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)
+            return fused.backward(plan, dout, q, k, v, out, lse, scale, group, ordered)
         rep = q.shape[1] // k.shape[1]
         dqs, dks, dvs = [], [], []
         for h0 in range(0, k.shape[1], g):
             qs = slice(h0 * rep, (h0 + g) * rep)
             dq_g, dk_g, dv_g = fused.backward(plan, dout[:, qs], q[:, qs], k[:, h0:h0 + g], v[:, h0:h0 + g],
-                                              out[:, qs], lse[qs], scale, group, deterministic)
+                                              out[:, qs], lse[qs], scale, group, ordered)
             dqs.append(dq_g)
             dks.append(dk_g)
             dvs.append(dv_g)
         return torch.cat(dqs, dim=1), torch.cat(dks, dim=1), torch.cat(dvs, dim=1)
     if transport == "allgather":
-        return allgather_backward(plan, dout, q, k, v, out, lse, scale, group, heads_k_stride, deterministic)
-    return ring_backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)
+        return allgather_backward(plan, dout, q, k, v, out, lse, scale, group, heads_k_stride, ordered)
+    return ring_backward(plan, dout, q, k, v, out, lse, scale, group, ordered)

@@ -42,19 +42,21 @@ def _forward_local(plan: CPPlan, q, k, v, scale):
     return attn_cuda.forward_launch(q, k, v, items, segs, covered, scale)
 
 
-def _backward_local(plan: CPPlan, dout, q, k, v, out, lse, scale):
+def _backward_local(plan: CPPlan, dout, q, k, v, out, lse, scale, deterministic=False):
     delta = attn_cuda.compute_delta(out, dout)
     dq = attn_cuda.dq_workspace.acquire(q)  # zeroed fp32 accumulator, re-zeroed by dq_finalize
     if attn_cuda.has_window(plan.segments):
         # windowed tables may leave key tiles without any query: start from zeros (model dtype)
         dk, dv = torch.zeros_like(k), torch.zeros_like(v)
-        attn_cuda.segments_backward(plan, plan.segments, dout, q, k, v, lse, delta, scale, dq, dk, dv)
+        attn_cuda.segments_backward(plan, plan.segments, dout, q, k, v, lse, delta, scale, dq, dk, dv, deterministic)
     else:
-        items, qsegs = attn_cuda.bwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",))
+        items, qsegs, *bounds = attn_cuda.bwd_tables(plan, plan.segments, {plan.rank: 0}, q.device, ("local",),
+                                                     ordered=deterministic)
         # every key tile has exactly one writer and the epilogue stores the model dtype: no memset, no cast
         alloc = torch.empty_like if attn_cuda.bwd_tables_cover(plan, q.device, ("local",)) else torch.zeros_like
         dk, dv = alloc(k), alloc(v)
-        attn_cuda.backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq, dk, dv)
+        attn_cuda.backward_launch(q, dout, k, v, lse, delta, items, qsegs, scale, dq, dk, dv,
+                                  bounds[0] if bounds else None)
     return attn_cuda.dq_workspace.finalize(dq, q), dk, dv
 
 
@@ -68,7 +70,7 @@ def forward(plan: CPPlan, q, k, v, scale, group):
 
 def backward(plan: CPPlan, dout, q, k, v, out, lse, scale, group, deterministic=False):
     if plan.world == 1:
-        return _backward_local(plan, dout, q, k, v, out, lse, scale)
+        return _backward_local(plan, dout, q, k, v, out, lse, scale, deterministic)
     from . import symm
 
     return symm.fused_backward(plan, dout, q, k, v, out, lse, scale, group, deterministic)

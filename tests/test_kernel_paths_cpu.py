@@ -160,3 +160,81 @@ def _fp8_case(rank, world):
 @pytest.mark.parametrize("world", [1, 2])
 def test_fp8_launch_path(world):
     run_distributed(_fp8_case, world)
+
+
+def test_ordered_dq_groups_are_conflict_free():
+    """deterministic=True: key tiles of one launch group never reach the same query rows; every tile is launched once."""
+    from ring_flash_attn_b200.ops import attn_cuda
+    from ring_flash_attn_b200.parallel import ops as O
+
+    def spans(it, qsegs):
+        return [(r0 + max(0, -d), r0 + n) for r0, n, d, _ in qsegs[it[2]:it[2] + it[3]] if max(0, -d) < n]
+
+    def check(plan, window=False):
+        if window:
+            items, qsegs = attn_cuda.bwd_tables_window_host(plan, plan.segments, {plan.rank: 0})
+        else:
+            items, qsegs = attn_cuda.bwd_tables_host(plan, plan.segments, {plan.rank: 0})
+        ordered, bounds = attn_cuda.ordered_dq_groups(items, qsegs)
+        assert sorted(map(tuple, ordered)) == sorted(map(tuple, items)) and bounds[0] == 0 and bounds[-1] == len(items)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            assert b > a
+            taken = sorted(s for it in ordered[a:b] for s in spans(it, qsegs))
+            assert all(x[1] <= y[0] for x, y in zip(taken[:-1], taken[1:])), (a, b, taken)
+        return len(items), len(bounds) - 1
+
+    n, g = check(O.batch_plan("zigzag", 0, 1, 1, 1024, True))
+    assert n == 8 and g == 8  # one causal sequence: every key tile reaches the last query rows
+    n, g = check(O.batch_plan("zigzag", 0, 1, 4, 512, True))
+    assert n == 16 and g == 4  # four batch elements side by side
+    n, g = check(O.batch_plan("ring", 0, 1, 1, 1024, True, (200, 0)), window=True)
+    assert n == 8 and 2 <= g <= 3  # a 200-token window: a query row is reached by at most 3 key tiles
+    n, g = check(O.varlen_plan("ring", 0, 1, (0, 100, 700, 701, 1500), True))
+    assert g == 7  # the longest document (799 keys) has 7 key tiles; the other documents ride along
+
+
+def _deterministic_case(rank, world):
+    import fake_ext
+
+    os.environ["RFA_B200_DISABLE_P2P"] = "1"
+    fake = fake_ext.install()
+    torch.manual_seed(1)
+    S, H, d = 384 * world, 2, 64
+    qkv = torch.randn(2, S, 3, H, d).to(torch.bfloat16)
+    dout = torch.randn(2, S, H, d).to(torch.bfloat16)
+    if world > 1:
+        dist.broadcast(qkv, src=0)
+        dist.broadcast(dout, src=0)
+    local = layouts.shard_zigzag(qkv, rank, world)
+    grads, launches = [], []
+    for det in (False, True):
+        x = local.detach().requires_grad_(True)
+        fake.calls.clear()
+        with pytest.warns(RuntimeWarning, match="deterministic=True") if det and not _deterministic_case.warned \
+                else __import__("contextlib").nullcontext():
+            out = rfa.zigzag_ring_flash_attn_qkvpacked_func(x, causal=True, deterministic=det)
+            out.backward(layouts.shard_zigzag(dout, rank, world))
+        _deterministic_case.warned |= det
+        grads.append(x.grad.clone())
+        launches.append(fake.calls.count("attn_bwd"))
+    torch.testing.assert_close(grads[0].float(), grads[1].float(), atol=2e-2, rtol=2e-2)
+    # world 1: 2 x 384 local rows = 3 key tiles per batch element -> 3 groups of 2 tiles instead of one launch;
+    # world 2: one launch per source before, one per group and source now
+    assert launches[0] == world and launches[1] > launches[0], launches
+    os.environ["RFA_B200_DETERMINISTIC"] = "fast"
+    try:
+        x = local.detach().requires_grad_(True)
+        fake.calls.clear()
+        rfa.zigzag_ring_flash_attn_qkvpacked_func(x, causal=True, deterministic=True).backward(
+            layouts.shard_zigzag(dout, rank, world))
+        assert fake.calls.count("attn_bwd") == world
+    finally:
+        os.environ.pop("RFA_B200_DETERMINISTIC", None)
+
+
+_deterministic_case.warned = False
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_deterministic_backward_launch_groups(world):
+    run_distributed(_deterministic_case, world)
