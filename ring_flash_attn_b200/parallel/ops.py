@@ -23,6 +23,7 @@ import torch.distributed as dist
 from torch import Tensor
 
 from ..ops import plan as P
+from ..utils import trace
 from . import engine
 from .comm import group_info
 
@@ -179,6 +180,11 @@ def cp_attn_fwd(q: Tensor, k: Tensor, v: Tensor, cu_a: Optional[Tensor], cu_b: O
     bf16 / fp16): one fp32 per block of T / nq (T / nk) consecutive token-major rows and head."""
     pg = resolve_group(group)
     plan, transport, stride = resolve_plan(scheme, spec, cu_a, cu_b, q.shape[0], pg)
+    with trace.nvtx(f"rfa.{scheme}.fwd", q):
+        return _cp_attn_fwd_impl(plan, transport, stride, pg, q, k, v, scale_q, scale_k, scale_v, softmax_scale)
+
+
+def _cp_attn_fwd_impl(plan, transport, stride, pg, q, k, v, scale_q, scale_k, scale_v, softmax_scale):
     if scale_q is not None:
         from ..ops import attn_cuda
 
@@ -207,7 +213,8 @@ def cp_attn_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, out: Tensor, lse:
                 deterministic: bool) -> Tuple[Tensor, Tensor, Tensor]:
     pg = resolve_group(group)
     plan, transport, stride = resolve_plan(scheme, spec, cu_a, cu_b, q.shape[0], pg)
-    return engine.cp_backward(plan, dout, q, k, v, out, lse, softmax_scale, pg, transport, stride, deterministic)
+    with trace.nvtx(f"rfa.{scheme}.bwd", q):
+        return engine.cp_backward(plan, dout, q, k, v, out, lse, softmax_scale, pg, transport, stride, deterministic)
 
 
 @cp_attn_bwd.register_fake

@@ -160,3 +160,16 @@ def test_fp8_scale_tables_follow_rows():
     h = allr.heads(slice(1, 2), slice(1, 2))
     assert h.q.shape == (4, 1) and h.k.shape == (6, 1) and h.v_ref.tolist() == [5.0] and h.kv_row0 == 384
     assert len(allr.args()) == 7
+
+
+def test_nvtx_ranges_are_free_on_cpu(monkeypatch):
+    import torch
+
+    from ring_flash_attn_b200.utils import trace
+
+    monkeypatch.setenv("RFA_B200_NVTX", "1")
+    assert trace.enabled()
+    with trace.nvtx("rfa.test", torch.zeros(1)):  # CPU tensor: no CUDA call is made
+        pass
+    monkeypatch.delenv("RFA_B200_NVTX")
+    assert not trace.enabled()
