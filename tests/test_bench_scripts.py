@@ -98,3 +98,12 @@ def test_prefetched_e2e_loop_pipelines_one_copy_per_step():
     assert [v for v, _ in seen] == [0.0, 1.0, 2.0, 3.0, 4.0]
     ptrs = [p for _, p in seen]
     assert ptrs[0] == ptrs[2] == ptrs[4] and ptrs[1] == ptrs[3] and ptrs[0] != ptrs[1]  # double buffer alternates
+
+
+def test_minimal_example_world2():
+    """examples/ring_attention_minimal.py: shard, attend, backward, sampled fp32 check - on gloo."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29693", os.path.join(ROOT, "examples", "ring_attention_minimal.py"),
+           "--scheme", "stripe", "--head-dim", "64"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "ok=True" in r.stdout, r.stdout[-2000:]
