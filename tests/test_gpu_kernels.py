@@ -396,3 +396,19 @@ def test_fp8_forward_block_scaled(q_block, kv_block):
     torch.testing.assert_close(lse, ref_lse, atol=2e-2, rtol=2e-2)
     err = (out.float() - ref).abs().max().item()
     assert err < 6e-2 * ref.abs().max().item() + 2e-2, err
+
+
+def test_headline_shape_sampled_oracle_1gpu():
+    """bench.py's shape at one GPU (S = 32768, 32 heads of 128, zigzag qkvpacked fwd + bwd) on sampled rows / heads
+    against the fp32 oracle (utils/verify.py) - what ``bench.py --check`` prints, as a test."""
+    from ring_flash_attn_b200.utils.verify import sampled_check
+
+    torch.manual_seed(0)
+    qkv = torch.randn(1, 32768, 3, 32, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(1, 32768, 32, 128, device="cuda").to(torch.bfloat16)
+    out, lse, _ = rfa.zigzag_ring_flash_attn_qkvpacked_func(qkv, causal=True, return_attn_probs=True)
+    out.backward(dout)
+    g, x = qkv.grad[0], qkv.detach()[0]
+    res = sampled_check("zigzag", x[:, 0], x[:, 1], x[:, 2], dout[0], out.detach()[0], lse[0], g[:, 0], g[:, 1], g[:, 2],
+                        kv_heads=[0, 17, 31])
+    assert res["ok"], res

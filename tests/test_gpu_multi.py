@@ -295,6 +295,35 @@ def test_compiled_schemes_2gpu():
     run_distributed(_compiled_case, 2, backend="nccl")
 
 
+def _headline_shape(rank, world):
+    """The benchmark shape itself (zigzag qkvpacked, 4096 local tokens, 32 heads of 128, fwd + bwd) against the fp32
+    oracle on sampled rows and heads (utils/verify.py) - a dense oracle of 32768 x 32768 x 32 does not fit.  Same
+    check as ``bench.py --check``; here it fails the test tier instead of printing a flag."""
+    from ring_flash_attn_b200.utils.verify import sampled_check
+
+    os.environ["RFA_B200_DISABLE_P2P"] = "0"
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(100 + rank)  # every rank owns different data: the oracle gathers the shards
+    s_local, h = 4096, 32
+    for _ in range(2):  # second call: other staging parity, epochs advanced
+        qkv = torch.randn(1, s_local, 3, h, 128, device=dev).to(torch.bfloat16).requires_grad_(True)
+        dout = torch.randn(1, s_local, h, 128, device=dev).to(torch.bfloat16)
+        out, lse, _ = rfa.zigzag_ring_flash_attn_qkvpacked_func(qkv, causal=True, return_attn_probs=True)
+        out.backward(dout)
+        g = qkv.grad[0]
+        x = qkv.detach()[0]
+        res = sampled_check("zigzag", x[:, 0], x[:, 1], x[:, 2], dout[0], out.detach()[0], lse[0], g[:, 0], g[:, 1],
+                            g[:, 2], kv_heads=[0, 13, 31])
+        assert res["ok"], res
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_headline_shape_sampled_oracle(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    run_distributed(_headline_shape, world, backend="nccl")
+
+
 def _llama3_strict_groups(rank, world):
     """heads_k_stride honoured literally (RFA_B200_LLAMA3_HEAD_GROUPS=strict): one fused launch per kv head, staging
     sized for one head; also a hand-built (cloned) cu_seqlens - no attribute of prepare()'s tensors is needed."""
