@@ -173,3 +173,39 @@ def test_nvtx_ranges_are_free_on_cpu(monkeypatch):
         pass
     monkeypatch.delenv("RFA_B200_NVTX")
     assert not trace.enabled()
+
+
+def test_packed_inputs_get_one_concatenated_gradient():
+    """qkv / kv packed entry points: the slices are views, their gradient is a single stack (no zero-fill + add per
+    slice), and it equals the gradient of the unpacked call."""
+    import torch
+
+    import ring_flash_attn_b200 as rfa
+
+    torch.manual_seed(0)
+    qkv = torch.randn(2, 96, 3, 2, 32)
+    dout = torch.randn(2, 96, 2, 32)
+    a = qkv.clone().requires_grad_(True)
+    out = rfa.ring_flash_attn_qkvpacked_func(a, causal=True)
+    node = out.grad_fn
+    names = set()
+    stack = [node]
+    while stack:
+        n = stack.pop()
+        if n is None or n.name() in names and n.name() != "torch::autograd::AccumulateGrad":
+            continue
+        names.add(n.name())
+        stack.extend(f for f, _ in n.next_functions)
+    assert any("_Unpack" in n for n in names) and not any("Select" in n or "Unbind" in n for n in names), names
+    out.backward(dout)
+    q, k, v = (qkv[:, :, i].clone().requires_grad_(True) for i in range(3))
+    rfa.ring_flash_attn_func(q, k, v, causal=True).backward(dout)
+    torch.testing.assert_close(a.grad, torch.stack((q.grad, k.grad, v.grad), dim=2))
+    # kv packed, varlen layout, only kv requires grad
+    kv = torch.randn(96, 2, 2, 32, requires_grad=True)
+    qq = torch.randn(96, 2, 32)
+    cu = torch.tensor([0, 40, 96], dtype=torch.int32)
+    rfa.ring_flash_attn_varlen_kvpacked_func(qq, kv, cu, 56, causal=True).sum().backward()
+    assert kv.grad.shape == kv.shape and torch.isfinite(kv.grad).all()
+    with torch.no_grad():  # no autograd: plain views
+        assert rfa.ring_flash_attn_qkvpacked_func(qkv, causal=True).shape == (2, 96, 2, 32)
