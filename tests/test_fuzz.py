@@ -1,0 +1,25 @@
+"""A few fixed seeds of the randomised cases in ``tests/fuzz_cases.py`` (long runs: ``python tests/fuzz_cases.py``)."""
+import pytest
+
+import fuzz_cases
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    import fake_ext
+    from ring_flash_attn_b200.ops import cuda_ext
+
+    monkeypatch.setattr(cuda_ext, "load", cuda_ext.load)  # restored after the test
+    monkeypatch.setattr(cuda_ext, "available_for", cuda_ext.available_for)
+    return fake_ext.install()
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+@pytest.mark.parametrize("seed", range(1000, 1024))
+def test_world1_random_case(fake, seed):
+    fuzz_cases.world1_case(seed)
+
+
+@pytest.mark.parametrize("seed", range(2000, 2006))
+def test_fused_replay_random_case(seed):
+    fuzz_cases.fused_case(seed)
