@@ -7,8 +7,11 @@
 * ``fused_case(seed)``: the fused multi-GPU launch replayed in one process (``tests/test_fused_emulation.py``) for a
   random scheme / world size / shard length / window / packing.
 
+* ``dist_worker(...)``: the torch.distributed transports inside a spawned gloo world (per-source launches or dense
+  blocks), every scheme incl. llama3 with ``heads_k_stride``.
+
 ``tests/test_fuzz.py`` runs a few fixed seeds; ``python tests/fuzz_cases.py world1|fused <first seed> <seconds>`` runs
-until the time is up (round 2: 626 + 228 cases, no failure).
+until the time is up (round 2: 626 world-1, 228 fused-replay and 240 distributed cases, no failure).
 """
 import os
 import random
@@ -155,6 +158,92 @@ def fused_case(seed: int):
         return desc + (cu,)
     finally:
         E.D = old_d
+
+
+def dist_worker(rank: int, world: int, seed0: int, ncases: int, use_fake: bool):
+    """Random cases over the torch.distributed transports inside a spawned world (``dist_utils.run_distributed``):
+    per-source launches of the table-driven contract (``use_fake``, bf16) or the dense fp32 blocks; batch schemes,
+    varlen, llama3 (with ``heads_k_stride``), zigzag-llama3; windows; ordered mode."""
+    warnings.simplefilter("ignore")
+    os.environ["RFA_B200_DISABLE_P2P"] = "1"
+    if use_fake:
+        import fake_ext
+
+        fake_ext.install()
+    dt = torch.bfloat16 if use_fake else torch.float32
+    for seed in range(seed0, seed0 + ncases):
+        rnd = random.Random(seed)
+        torch.manual_seed(seed)
+        hkv = rnd.choice([1, 2])
+        hq = hkv * rnd.choice([1, 2, 4])
+        d = rnd.choice([32, 64, 128]) if use_fake else rnd.choice([16, 32])
+        det = rnd.random() < 0.5
+        window = rnd.choice([(-1, -1), (-1, -1), (rnd.randint(0, 400), 0)])
+        kind = rnd.choice(["ring", "zigzag", "stripe", "ring_varlen", "zigzag_varlen", "llama3", "zzl3"])
+        causal = True if kind not in ("ring", "ring_varlen") else rnd.random() < 0.6
+        if not causal:
+            window = (-1, -1) if rnd.random() < 0.5 else (rnd.randint(0, 300), rnd.randint(0, 300))
+        if kind in ("ring", "zigzag", "stripe"):
+            B = rnd.choice([1, 2])
+            S = world * rnd.choice([32, 64, 130, 2 * rnd.randint(1, 150)])
+            q, kv, dout = torch.randn(B, S, hq, d).to(dt), torch.randn(B, S, 2, hkv, d).to(dt), torch.randn(B, S, hq, d).to(dt)
+            shard = getattr(layouts, f"shard_{kind}")
+            x = shard(q, rank, world).clone().requires_grad_(True)
+            y = shard(kv, rank, world).clone().requires_grad_(True)
+            prefix = {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}[kind]
+            out = getattr(rfa, prefix + "_flash_attn_kvpacked_func")(x, y, causal=causal, window_size=window,
+                                                                     deterministic=det)
+            out.backward(shard(dout, rank, world))
+            rq, rkv = q.clone().float().requires_grad_(True), kv.clone().float().requires_grad_(True)
+            ref, _ = attention_oracle(rq, rkv[:, :, 0], rkv[:, :, 1], causal, window_size=window)
+            ref.backward(dout.float())
+            _close(out, shard(ref, rank, world), f"{seed} out")
+            _close(x.grad, shard(rq.grad, rank, world), f"{seed} dq")
+            _close(y.grad, shard(rkv.grad, rank, world), f"{seed} dkv")
+            continue
+        ndoc = rnd.randint(1, 4)
+        if kind in ("llama3", "zzl3"):
+            T = 2 * world * rnd.randint(4, 120)
+            cuts = sorted(rnd.sample(range(1, T), min(ndoc - 1, T - 1)))
+        else:
+            unit, nunits = 2 * world, rnd.randint(ndoc, 60)
+            T = unit * nunits
+            cuts = sorted({unit * c for c in rnd.sample(range(1, nunits), min(ndoc - 1, nunits - 1))}) if nunits > 1 else []
+        cu = [0] + cuts + [T]
+        cu_t = torch.tensor(cu, dtype=torch.int32)
+        q, k, v = (torch.randn(T, h, d).to(dt) for h in (hq, hkv, hkv))
+        dout = torch.randn(T, hq, d).to(dt)
+        rs = [t.clone().float().requires_grad_(True) for t in (q, k, v)]
+        ref, _ = varlen_attention_oracle(*rs, cu_t, causal, window_size=window)
+        ref.backward(dout.float())
+        if kind == "zzl3":
+            def sh(t):
+                return layouts.shard_zigzag_llama3(t, rank, world)
+
+            xs = [sh(t).clone().requires_grad_(True) for t in (q, k, v)]
+            out = rfa.zigzag_llama3_flash_attn_varlen_func(*xs, cu_t, causal=True, window_size=window, deterministic=det)
+        elif kind == "llama3":
+            def sh(t):
+                return layouts.shard_llama3(t, rank, world)
+
+            xs = [sh(t).clone().requires_grad_(True) for t in (q, k, v)]
+            cq, ck, mq, mk, ks = rfa.llama3_flash_attn_prepare_cu_seqlens(cu_t, True, rank, world)
+            out = rfa.llama3_flash_attn_varlen_func(*xs, cq, ck, mq, mk, heads_k_stride=rnd.choice([1, hkv]),
+                                                    local_k_slice=ks, causal=True, window_size=window, deterministic=det)
+        else:
+            which = "ring" if kind == "ring_varlen" else "zigzag"
+
+            def sh(t):
+                return getattr(layouts, f"shard_{which}_varlen")(t, cu, rank, world)
+
+            xs = [sh(t).clone().requires_grad_(True) for t in (q, k, v)]
+            lcu = cu_t // world
+            fn = rfa.ring_flash_attn_varlen_func if which == "ring" else rfa.zigzag_ring_flash_attn_varlen_func
+            out = fn(*xs, lcu, int((lcu[1:] - lcu[:-1]).max()), causal=causal, window_size=window, deterministic=det)
+        out.backward(sh(dout))
+        _close(out, sh(ref), f"{seed} out")
+        for a, b, nm in zip(xs, rs, "qkv"):
+            _close(a.grad, sh(b.grad), f"{seed} d{nm}")
 
 
 def main():

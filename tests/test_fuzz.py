@@ -23,3 +23,10 @@ def test_world1_random_case(fake, seed):
 @pytest.mark.parametrize("seed", range(2000, 2006))
 def test_fused_replay_random_case(seed):
     fuzz_cases.fused_case(seed)
+
+
+@pytest.mark.parametrize("world,seed0,n,use_fake", [(3, 5000, 8, True), (2, 6000, 6, False)])
+def test_distributed_random_cases(world, seed0, n, use_fake):
+    from dist_utils import run_distributed
+
+    run_distributed(fuzz_cases.dist_worker, world, seed0, n, use_fake)
