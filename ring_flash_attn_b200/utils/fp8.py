@@ -1,12 +1,14 @@
 """Block-scaled fp8 inputs (extension; the reference has no fp8 path).
 
-BASELINE.json config 5 asks for stripe attention on block-scaled fp8 Q/K/V.  Round 1 ships the *interface* and a
-correct reference implementation: fp8 (e4m3 / e5m2) tensors travel with a ``descale`` tensor and are expanded
-to bf16 right before the attention call; the tensor-core math itself is still bf16 (a ``kind::f8f6f4`` /
-``mxf8f6f4`` variant of the forward kernel is the planned follow-up).  The scale layout is
-deliberately general: ``descale.shape[d]`` must divide ``x.shape[d]`` in every dimension, the quotient is the
-block size along that dimension.  This covers per-tensor, per-head, per-token-block (e.g. 128 tokens) and
-MX-style per-32-element scaling (``float8_e8m0fnu`` scales are accepted as well).
+BASELINE.json config 5 asks for stripe attention on block-scaled fp8 Q/K/V.  fp8 (e4m3 / e5m2) tensors travel with a
+``descale`` tensor.  e4m3 q / k / v of head size 128 whose descales are per tensor, per head or per token block x head
+(k / v: blocks that are whole 128-key tiles) go straight into the fp8 forward kernel (``kind::f8f6f4``, one byte per
+element on the NVLink wire, scales applied to the fp32 scores / folded into P; ``parallel/api.py:_fp8_kernel_scales``,
+``csrc/attn_fwd_sm100.cu``); everything else (e5m2, scales that vary inside a row such as MX per-32 along head_dim,
+sliding windows, other head sizes) is expanded to bf16 right before the attention call.  The scale layout is
+deliberately general: ``descale.shape[d]`` must divide ``x.shape[d]`` in every dimension, the quotient is the block
+size along that dimension (``float8_e8m0fnu`` scales are accepted as well).  Forward only: fp8 tensors carry no
+gradient.
 """
 from __future__ import annotations
 
@@ -65,8 +67,8 @@ def quantize_blockwise(x: torch.Tensor, block: Sequence[int], dtype: torch.dtype
 
 def quantize_per_head(x: torch.Tensor, keep_dims: Sequence[int] = (), dtype: torch.dtype = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """One descale per head (heads at dim -2), plus one per index of every dim listed in ``keep_dims`` (e.g. the
-    pack dim of a kv / qkv tensor).  This is the granularity the fp8 forward kernel consumes natively
-    (``RFA_B200_FP8_KERNEL=1``); finer block scales are dequantised to bf16 in front of the kernels.
+    pack dim of a kv / qkv tensor).  The coarsest granularity the fp8 forward kernel consumes natively; token-block x
+    head scales (``quantize_blockwise(x, [1, 128, 1, 0])``) are native as well, scales along head_dim are not.
 
         q8, dq = quantize_per_head(q)                       # q (B, S, H, D)       -> dq (1, 1, H, 1)
         kv8, dkv = quantize_per_head(kv, keep_dims=(2,))    # kv (B, S, 2, Hkv, D) -> dkv (1, 1, 2, Hkv, 1)

@@ -30,3 +30,10 @@ def test_distributed_random_cases(world, seed0, n, use_fake):
     from dist_utils import run_distributed
 
     run_distributed(fuzz_cases.dist_worker, world, seed0, n, use_fake)
+
+
+@pytest.mark.parametrize("world,seed0,n", [(1, 7000, 10), (2, 7100, 8)])
+def test_fp8_random_descale_layouts(world, seed0, n):
+    from dist_utils import run_distributed
+
+    run_distributed(fuzz_cases.fp8_worker, world, seed0, n)
