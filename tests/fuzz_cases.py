@@ -249,57 +249,72 @@ def dist_worker(rank: int, world: int, seed0: int, ncases: int, use_fake: bool):
 def fp8_worker(rank, world, seed0, n):
     """Random fp8 descale layouts (per tensor / head / token block / MX along head_dim) x schemes x entry points:
     either the fp8 launch contract (``attn_fwd_fp8`` with its scale tables) or the dequantise-to-bf16 path must match
-    attention on the dequantised values of every rank."""
+    attention on the dequantised values of every rank.  Returns how many cases took which path."""
     import torch.distributed as dist
+
     import fake_ext
     from ring_flash_attn_b200.utils import fp8
+
     warnings.simplefilter("ignore")
     os.environ["RFA_B200_DISABLE_P2P"] = "1"
     fake = fake_ext.install()
     counts = {"kernel": 0, "dequant": 0}
+    prefixes = {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}
+
+    def gather(t, scheme):
+        parts = [torch.empty_like(t.contiguous()) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        return layouts.unshard(scheme, parts, dim=1)
+
     for seed in range(seed0, seed0 + n):
-        rnd = random.Random(seed); torch.manual_seed(seed)
+        rnd = random.Random(seed)
+        torch.manual_seed(seed)
         os.environ["RFA_B200_FP8_KERNEL"] = rnd.choice(["1", "2", "2", "0"])
-        hkv = rnd.choice([1, 2]); hq = hkv * rnd.choice([1, 2]); d = rnd.choice([128, 128, 64])
+        hkv = rnd.choice([1, 2])
+        hq = hkv * rnd.choice([1, 2])
+        d = rnd.choice([128, 128, 64])
         scheme = rnd.choice(["ring", "zigzag", "stripe"])
-        B = rnd.choice([1, 2]); L = rnd.choice([128, 256, 384, 200, 512]); S = L * world
-        api = rnd.choice(["func", "kvpacked", "qkvpacked"])
-        if api == "qkvpacked": hq = hkv
-        tb = rnd.choice([0, 128, 64, L, 1 if L <= 256 else 128, 256 if L % 256 == 0 else 128])  # token block (0 = whole)
-        per_head = rnd.choice([0, 1])   # block along heads: 0 whole / 1 per head
-        dblk = rnd.choice([0, 0, 0, 32])  # MX-style along head_dim sometimes
-        q = torch.randn(B, S, hq, d) * (1 + 2 * torch.rand(B, S, 1, 1)); kv = torch.randn(B, S, 2, hkv, d) * (1 + torch.rand(B, S, 1, 1, 1))
-        dist.broadcast(q, src=0); dist.broadcast(kv, src=0)
+        B = rnd.choice([1, 2])
+        L = rnd.choice([128, 256, 384, 200, 512])
+        S = L * world
+        entry = rnd.choice(["func", "kvpacked", "qkvpacked"])
+        if entry == "qkvpacked":
+            hq = hkv
+        tb = rnd.choice([0, 128, 64, L, 1 if L <= 256 else 128, 256 if L % 256 == 0 else 128])  # tokens per block, 0 = all
+        if tb and L % tb:
+            tb = 0
+        per_head = rnd.choice([0, 1])      # 0: one scale for all heads, 1: one per head
+        dblk = rnd.choice([0, 0, 0, 32])   # sometimes MX-style blocks along head_dim
+        per_batch = 1 if tb else 0
+        q = torch.randn(B, S, hq, d) * (1 + 2 * torch.rand(B, S, 1, 1))
+        kv = torch.randn(B, S, 2, hkv, d) * (1 + torch.rand(B, S, 1, 1, 1))
+        dist.broadcast(q, src=0)
+        dist.broadcast(kv, src=0)
         shard = getattr(layouts, f"shard_{scheme}")
         lq, lkv = shard(q, rank, world), shard(kv, rank, world)
-        if tb and L % tb: tb = 0
-        bq = [1 if False else 0, tb, per_head, dblk]; bq[0] = 1 if tb else 0
-        bkv = [bq[0], tb, 1, per_head, dblk]
-        desc = (seed, scheme, world, api, B, L, hq, hkv, d, tb, per_head, dblk, os.environ["RFA_B200_FP8_KERNEL"])
+        desc = (seed, scheme, world, entry, B, L, hq, hkv, d, tb, per_head, dblk, os.environ["RFA_B200_FP8_KERNEL"])
         fake.calls.clear()
-        if api == "qkvpacked":
-            lqkv = torch.cat([lq.unsqueeze(2), lkv], dim=2)
-            x8, sc = fp8.quantize_blockwise(lqkv, [bq[0], tb, 1, per_head, dblk])
+        if entry == "qkvpacked":
+            x8, sc = fp8.quantize_blockwise(torch.cat([lq.unsqueeze(2), lkv], dim=2), [per_batch, tb, 1, per_head, dblk])
             deq = fp8.dequantize(x8, sc, torch.float32)
             dq_, dk_, dv_ = deq[:, :, 0], deq[:, :, 1], deq[:, :, 2]
-            out = getattr(rfa, {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}[scheme] + "_flash_attn_qkvpacked_func")(x8, causal=True, descale=sc)
+            out = getattr(rfa, prefixes[scheme] + "_flash_attn_qkvpacked_func")(x8, causal=True, descale=sc)
         else:
-            q8, sq = fp8.quantize_blockwise(lq, bq); kv8, skv = fp8.quantize_blockwise(lkv, bkv)
-            dq_ = fp8.dequantize(q8, sq, torch.float32); dkv_ = fp8.dequantize(kv8, skv, torch.float32); dk_, dv_ = dkv_[:, :, 0], dkv_[:, :, 1]
-            pre = {"ring": "ring", "zigzag": "zigzag_ring", "stripe": "stripe"}[scheme]
-            if api == "kvpacked":
-                out = getattr(rfa, pre + "_flash_attn_kvpacked_func")(q8, kv8, causal=True, descale=(sq, skv))
+            q8, sq = fp8.quantize_blockwise(lq, [per_batch, tb, per_head, dblk])
+            kv8, skv = fp8.quantize_blockwise(lkv, [per_batch, tb, 1, per_head, dblk])
+            dq_ = fp8.dequantize(q8, sq, torch.float32)
+            dkv_ = fp8.dequantize(kv8, skv, torch.float32)
+            dk_, dv_ = dkv_[:, :, 0], dkv_[:, :, 1]
+            if entry == "kvpacked":
+                out = getattr(rfa, prefixes[scheme] + "_flash_attn_kvpacked_func")(q8, kv8, causal=True, descale=(sq, skv))
             else:
-                out = getattr(rfa, pre + "_flash_attn_func")(q8, kv8[:, :, 0], kv8[:, :, 1], causal=True, descale=(sq, skv[:, :, 0], skv[:, :, 1]))
+                out = getattr(rfa, prefixes[scheme] + "_flash_attn_func")(
+                    q8, kv8[:, :, 0], kv8[:, :, 1], causal=True, descale=(sq, skv[:, :, 0], skv[:, :, 1]))
         counts["kernel" if "attn_fwd_fp8" in fake.calls else "dequant"] += 1
-        def gather(t):
-            parts = [torch.empty_like(t.contiguous()) for _ in range(world)]
-            dist.all_gather(parts, t.contiguous()); return layouts.unshard(scheme, parts, dim=1)
-        fq, fk, fv = gather(dq_), gather(dk_), gather(dv_)
-        ref, _ = attention_oracle(fq, fk, fv, True)
-        got, want = out.float(), shard(ref, rank, world)
-        err = (got - want).abs().max().item(); mag = want.abs().max().item()
-        assert out.dtype == torch.bfloat16 and err <= 3e-2 * mag + 2e-2, f"{desc}: err {err} vs {mag} calls {set(fake.calls)}"
+        ref, _ = attention_oracle(gather(dq_, scheme), gather(dk_, scheme), gather(dv_, scheme), True)
+        want = shard(ref, rank, world)
+        err, mag = (out.float() - want).abs().max().item(), want.abs().max().item()
+        assert out.dtype == torch.bfloat16 and err <= 3e-2 * mag + 2e-2, f"{desc}: err {err} vs {mag}, {set(fake.calls)}"
     return counts
 
 
