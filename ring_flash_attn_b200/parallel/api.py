@@ -87,8 +87,9 @@ class _Unpack(torch.autograd.Function):
 
 
 def _unpack(packed: torch.Tensor, dim: int):
-    """Slices of a packed qkv / kv tensor along ``dim`` (views, no copy)."""
-    if packed.requires_grad and torch.is_grad_enabled():
+    """Slices of a packed qkv / kv tensor along ``dim`` (views, no copy).  Under ``torch.compile`` the plain slices are
+    traced: the compiler fuses their backward itself."""
+    if packed.requires_grad and torch.is_grad_enabled() and not torch.compiler.is_compiling():
         return _Unpack.apply(packed, dim)
     return packed.unbind(dim)
 
