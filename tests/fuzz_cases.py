@@ -11,7 +11,7 @@
   blocks), every scheme incl. llama3 with ``heads_k_stride``.
 
 ``tests/test_fuzz.py`` runs a few fixed seeds; ``python tests/fuzz_cases.py world1|fused <first seed> <seconds>`` runs
-until the time is up (round 2: 626 world-1, 228 fused-replay and 240 distributed cases, no failure).
+until the time is up (round 2: 1591 world-1, 524 fused-replay, 430 distributed and 150 fp8 cases, no failure).
 """
 import os
 import random
