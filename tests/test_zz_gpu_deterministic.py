@@ -1,7 +1,8 @@
 """deterministic=True on the sm_100a path (B200): bitwise reproducible gradients, still equal to the fp32 oracle.
 
-Runs after every other GPU test file on purpose (the name sorts last): the launch-group schedule was written after the
-GPU budget of round 2 was spent, so this file is its first execution on hardware."""
+Passed on a B200 at the end of round 2 (profiles/r2/trip_last_deterministic.log).
+
+The file name sorts last so that the determinism checks run after every other GPU test file."""
 import pytest
 import torch
 
